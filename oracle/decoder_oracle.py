@@ -46,6 +46,7 @@ class DecoderConfig:
     final_logit_softcapping: float | None = None
     query_pre_attn_scalar: float | None = None
     tie_word_embeddings: bool = False
+    pad_token_id: int | None = None  # nn.Embedding(padding_idx=...) models/llama/modeling_llama.py:350-353
 
     @property
     def gemma(self) -> bool:
@@ -65,10 +66,10 @@ class DecoderConfig:
 
 
 # ------------------------------------------------------------------------------------------------------------- ops
-def embedding(ids: torch.Tensor, weight: torch.Tensor, scale: float | None = None) -> torch.Tensor:
+def embedding(ids: torch.Tensor, weight: torch.Tensor, scale: float | None = None, padding_idx: int | None = None) -> torch.Tensor:
     """nn.Embedding row gather, models/llama/modeling_llama.py:353,381 (bit-exact copy of weight rows).
     Gemma2TextScaledWordEmbedding models/gemma2/modeling_gemma2.py:338-349: * bf16(sqrt(hidden)) in weight dtype."""
-    out = F.embedding(ids, weight)
+    out = F.embedding(ids, weight, padding_idx=padding_idx)  # padding_idx only zeroes that row's gradient
     if scale is not None:
         out = out * torch.tensor(scale).to(weight.dtype)
     return out
@@ -278,7 +279,7 @@ def model_forward(ids: torch.Tensor, p: dict, cfg: DecoderConfig, labels: torch.
     w_emb = p["model.embed_tokens.weight"]
     dtype = w_emb.dtype
     scale = cfg.hidden_size**0.5 if cfg.gemma else None
-    h = embedding(ids, w_emb, scale)
+    h = embedding(ids, w_emb, scale, cfg.pad_token_id)
     position_ids = torch.arange(S)[None, :]
     cos, sin = rope_tables(rope_inv_freq(cfg), position_ids, dtype)
     masks = {}
@@ -316,4 +317,5 @@ def config_from_hf(hf_cfg) -> DecoderConfig:
         sliding_window=d.get("sliding_window"), layer_types=d.get("layer_types"),
         attn_logit_softcapping=d.get("attn_logit_softcapping"), final_logit_softcapping=d.get("final_logit_softcapping"),
         query_pre_attn_scalar=d.get("query_pre_attn_scalar"), tie_word_embeddings=bool(d.get("tie_word_embeddings", False)),
+        pad_token_id=d.get("pad_token_id"),
     )
