@@ -1,0 +1,88 @@
+/* b200_ops.h -- C ABI of libb200.so (transformers_b200/lib/libb200.so), the sm_100a kernels behind the reference's
+ * decoder hot path.  huggingface/transformers is pure Python: it has no native FFI of its own for this path, so every
+ * entry point below replaces a torch-op sequence of the reference (file:line given per function, relative to
+ * /root/reference/src/transformers) and is bound from Python with ctypes (transformers_b200/_lib.py; the binding a
+ * reference maintainer would add is shown in INTEGRATION.md).
+ *
+ * Conventions: all tensors are device pointers owned by the caller (bf16 unless noted); sizes are in elements; strides
+ * are in elements; every call is asynchronous on `stream`; return 0 on success, negative errno-style code otherwise
+ * (-22 invalid argument, -19 no sm_100 device, -5 CUDA error) with a message available from b200_last_error().
+ * Thread-compatible: no global mutable state except one-time function-attribute / driver-entry-point caches.
+ */
+#ifndef B200_OPS_H
+#define B200_OPS_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* b200_stream_t; /* == cudaStream_t */
+
+int b200_abi_version(void);
+int b200_device_check(void);           /* 0 iff the current device is sm_100 (B200) */
+const char* b200_last_error(void);     /* thread-local message of the last failing call */
+
+/* nn.Linear forward / dgrad / wgrad (models/llama/modeling_llama.py:174-176, :254-256, :280, :480):
+ * D[M,N] (+)= sum_k A(m,k) B(n,k); a_mn/b_mn = 0: operand stored [M|N, K]; 1: stored [K, M|N].  tcgen05 + TMA. */
+int b200_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
+                   int b_mn, int accumulate, b200_stream_t stream);
+int b200_gemm_bf16_ex(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
+                      int b_mn, int accumulate, int desc_variant, b200_stream_t stream);
+
+/* nn.Embedding gather / scatter-add (models/llama/modeling_llama.py:353,381; scaled variant
+ * models/gemma2/modeling_gemma2.py:338-349).  ids int64[T]; err_flag int32[1] set to 1 on out-of-range ids. */
+int b200_embedding_fwd(const int64_t* ids, const void* weight, void* out, int T, int H, int V, float scale,
+                       int has_scale, int* err_flag, b200_stream_t stream);
+int b200_embedding_bwd(const int64_t* ids, const void* dout, void* dweight, int T, int H, int V, int64_t padding_idx,
+                       float scale, int has_scale, b200_stream_t stream);
+
+/* LlamaRMSNorm.forward (models/llama/modeling_llama.py:62-67) / Gemma2RMSNorm (models/gemma2/modeling_gemma2.py:55-63),
+ * optionally fused with the preceding residual add (modeling_llama.py:317,323): res_out = bf16(x + res_in). */
+int b200_rmsnorm_fwd(const void* x, const void* res_in, const void* weight, void* res_out, void* y, float* rstd_out,
+                     int T, int H, float eps, int gemma, b200_stream_t stream);
+int b200_rmsnorm_bwd_workspace_rows(void); /* workspace = fp32[rows * H] */
+int b200_rmsnorm_bwd(const void* dy, const void* x, const void* weight, const float* rstd, void* dx, void* dweight,
+                     float* workspace, int T, int H, int gemma, int accumulate_dw, b200_stream_t stream);
+
+/* apply_rotary_pos_emb (models/llama/modeling_llama.py:130-160), in place on the packed projection buffer
+ * qkv[B*S, row_stride]; the first n_rot heads (q then k) are rotated; cos/sin bf16 [cos_batch, S, D]. */
+int b200_rope(void* qkv, const void* cos_t, const void* sin_t, int B, int S, int n_rot, int D, int row_stride,
+              int cos_batch, int bwd, b200_stream_t stream);
+
+/* LlamaMLP gate: act(gate) * up (models/llama/modeling_llama.py:174-176; activations.py:30-49, :92-103). */
+int b200_glu_fwd(const void* gate, const void* up, void* out, int T, int I, int ld_gu, int ld_out, int gelu,
+                 b200_stream_t stream);
+int b200_glu_bwd(const void* dh, const void* gate, const void* up, void* dgate, void* dup, int T, int I, int ld_dh,
+                 int ld_gu, int ld_dgu, int gelu, b200_stream_t stream);
+
+/* residual add (models/llama/modeling_llama.py:317,323) */
+int b200_add_bf16(const void* a, const void* b, void* out, int64_t n, b200_stream_t stream);
+
+/* Attention core (eager_attention_forward models/llama/modeling_llama.py:191-213; sdpa_attention_forward
+ * integrations/sdpa_attention.py:79-170; softcap branch models/gemma2/modeling_gemma2.py:201-208; masks
+ * masking_utils.py:76-101).  q [B,Sq,Hq,D], k/v [B,Skv,Hkv,D], out [B,Sq,Hq,D] as strided views given by
+ * (batch, row, head) strides; lse fp32 [B,Hq,lse_stride]; kv_start/kv_end optional int32[B] valid-kv ranges. */
+int b200_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int lse_stride, int B, int Sq,
+                  int Skv, int Hq, int Hkv, int D, int64_t q_bs, int64_t q_rs, int64_t q_hs, int64_t k_bs, int64_t k_rs,
+                  int64_t k_hs, int64_t v_bs, int64_t v_rs, int64_t v_hs, int64_t o_bs, int64_t o_rs, int64_t o_hs,
+                  float scale, float softcap, int causal, int window, const int* kv_start, const int* kv_end,
+                  b200_stream_t stream);
+/* strides: 8 tensors x (batch, row, head) for q, k, v, out, dout, dq, dk, dv; workspace fp32[2*B*Hq*lse_stride] */
+int b200_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse,
+                  void* dq, void* dk, void* dv, float* workspace, int B, int Sq, int Skv, int Hq, int Hkv, int D,
+                  int lse_stride, const int64_t* strides, float scale, float softcap, int causal, int window,
+                  const int* kv_start, const int* kv_end, b200_stream_t stream);
+
+/* ForCausalLMLoss (loss/loss_utils.py:32-70): shifted labels, fp32 log-sum-exp, mean over valid targets. */
+int b200_ce_fwd(const void* logits, const int64_t* labels, float* lse, float* loss_rows, float* loss_out,
+                float* denom_out, int B, int S, int V, int ld, int shift, int64_t ignore_index, float num_items,
+                b200_stream_t stream);
+int b200_ce_bwd(const void* logits, const int64_t* labels, const float* lse, const float* dloss, const float* denom,
+                void* dlogits, int B, int S, int V, int ld, int ld_out, int shift, int64_t ignore_index,
+                b200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_OPS_H */

@@ -41,7 +41,7 @@ def make_qkv(B, Sq, Skv, Hq, Hkv, D, packed, g):
 
 def call_fwd(q, k, v, out, lse, causal, window, softcap, ks=None, ke=None):
     B, Sq, Hq, D = q.shape; Skv, Hkv = k.shape[1], k.shape[2]
-    return lib.b200_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(), B, Sq, Skv, Hq, Hkv, D,
+    return lib.b200_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(), lse.shape[-1], B, Sq, Skv, Hq, Hkv, D,
                              q.stride(0), q.stride(1), q.stride(2), k.stride(0), k.stride(1), k.stride(2), v.stride(0), v.stride(1), v.stride(2),
                              out.stride(0), out.stride(1), out.stride(2), D ** -0.5, softcap, causal, window,
                              ks.data_ptr() if ks is not None else None, ke.data_ptr() if ke is not None else None, st())
@@ -50,7 +50,8 @@ def run_attn(B, Sq, Skv, Hq, Hkv, D, causal=1, window=0, softcap=0.0, packed=Fal
     g = torch.Generator(device=dev).manual_seed(seed)
     q, k, v = make_qkv(B, Sq, Skv, Hq, Hkv, D, packed, g)
     out = torch.empty(B, Sq, Hq, D, device=dev, dtype=torch.bfloat16)
-    lse = torch.empty(B, Hq, Sq, device=dev, dtype=torch.float32)
+    Sp = (Sq + 127) // 128 * 128
+    lse = torch.empty(B, Hq, Sp, device=dev, dtype=torch.float32)
     ks = ke = None
     if pad:
         ks = torch.tensor(([0, 5] + [0] * B)[:B], device=dev, dtype=torch.int32)
@@ -58,11 +59,27 @@ def run_attn(B, Sq, Skv, Hq, Hkv, D, causal=1, window=0, softcap=0.0, packed=Fal
     rc = call_fwd(q, k, v, out, lse, causal, window, softcap, ks, ke)
     if rc: return f"rc={rc} {_lib.last_error()}"
     torch.cuda.synchronize()
-    ro, rl = ref_attn(q, k, v, D ** -0.5, causal, window, softcap, ks, ke)
+    qr, kr_, vr = (t.detach().float().requires_grad_(True) for t in (q, k, v))
+    ro, rl = ref_attn(qr, kr_, vr, D ** -0.5, causal, window, softcap, ks, ke)
     eo = (out.float() - ro).abs().max().item()
     fin = torch.isfinite(rl)
-    el = (lse[fin] - rl[fin]).abs().max().item() if fin.any() else 0.0
-    return eo, el
+    el = (lse[..., :Sq][fin] - rl[fin]).abs().max().item() if fin.any() else 0.0
+    # backward
+    do = torch.randn(B, Sq, Hq, D, device=dev, generator=g).to(torch.bfloat16)
+    ro.backward(do.float())
+    dq = torch.full_like(q.contiguous(), float("nan")); dk = torch.full_like(k.contiguous(), float("nan")); dv = torch.full_like(v.contiguous(), float("nan"))
+    ws = torch.empty(2 * B * Hq * Sp, device=dev, dtype=torch.float32)
+    strides = []
+    for t in (q, k, v, out, do, dq, dk, dv): strides += [t.stride(0), t.stride(1), t.stride(2)]
+    import ctypes
+    sarr = (ctypes.c_int64 * 24)(*strides)
+    rc = lib.b200_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), do.data_ptr(), lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                           ws.data_ptr(), B, Sq, Skv, Hq, Hkv, D, Sp, ctypes.cast(sarr, ctypes.c_void_p), D ** -0.5, softcap, causal, window,
+                           ks.data_ptr() if ks is not None else None, ke.data_ptr() if ke is not None else None, st())
+    if rc: return f"bwd rc={rc} {_lib.last_error()}"
+    torch.cuda.synchronize()
+    rel = lambda a, r: ((a.float() - r).abs().max() / (r.abs().max() + 1e-6)).item()
+    return eo, el, rel(dq, qr.grad), rel(dk, kr_.grad), rel(dv, vr.grad)
 
 log(torch.cuda.get_device_name(0))
 cases = [
@@ -76,7 +93,7 @@ cases = [
 for c in cases:
     try: r = run_attn(**c)
     except Exception as e: r = f"EXC {e}"
-    ok = isinstance(r, tuple) and r[0] < 2e-2 and r[1] < 2e-2
+    ok = isinstance(r, tuple) and r[0] < 2e-2 and r[1] < 2e-2 and max(r[2:]) < 2e-2
     log("attn", c, "->", r, "OK" if ok else "FAIL")
 
 # timing at the Llama-3-8B shape
@@ -85,6 +102,15 @@ try:
     q, k, v = make_qkv(B, S, S, Hq, Hkv, D, True, torch.Generator(device=dev).manual_seed(1))
     out = torch.empty(B, S, Hq, D, device=dev, dtype=torch.bfloat16); lse = torch.empty(B, Hq, S, device=dev, dtype=torch.float32)
     f = lambda: call_fwd(q, k, v, out, lse, 1, 0, 0.0)
+    import ctypes
+    do = torch.randn(B, S, Hq, D, device=dev).to(torch.bfloat16)
+    dq = torch.empty_like(do); dk = torch.empty(B, S, Hkv, D, device=dev, dtype=torch.bfloat16); dv = torch.empty_like(dk)
+    ws = torch.empty(2 * B * Hq * S, device=dev, dtype=torch.float32)
+    strides = []
+    for t in (q, k, v, out, do, dq, dk, dv): strides += [t.stride(0), t.stride(1), t.stride(2)]
+    sarr = (ctypes.c_int64 * 24)(*strides)
+    fb = lambda: lib.b200_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), do.data_ptr(), lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                           ws.data_ptr(), B, S, S, Hq, Hkv, D, S, ctypes.cast(sarr, ctypes.c_void_p), D ** -0.5, 0.0, 1, 0, None, None, st())
     for _ in range(3): f()
     torch.cuda.synchronize(); e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -92,6 +118,11 @@ try:
     e1.record(); torch.cuda.synchronize(); ms = e0.elapsed_time(e1) / 10
     fl = 4.0 * B * Hq * S * S * D / 2
     log(f"attn fwd B4 S4096 H32/8 D128 causal: {ms:.3f} ms = {fl/ms/1e9:.0f} TF/s")
+    for _ in range(3): fb()
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(10): fb()
+    e1.record(); torch.cuda.synchronize(); msb = e0.elapsed_time(e1) / 10
+    log(f"attn bwd same shape: {msb:.3f} ms = {2.5*fl/msb/1e9:.0f} TF/s (5-matmul count), {3.5*fl/msb/1e9:.0f} TF/s executed")
     qt, kt, vt = q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)
     g = lambda: F.scaled_dot_product_attention(qt, kt, vt, is_causal=True, enable_gqa=True)
     for _ in range(3): g()

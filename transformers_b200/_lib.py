@@ -31,7 +31,8 @@ SIGNATURES = {
     "b200_glu_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "b200_add_bf16": [_p, _p, _p, _l, _p],
     "b200_ce_fwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _l, _f, _p],
-    "b200_attn_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i] + [_l] * 12 + [_f, _f, _i, _i, _p, _p, _p],
+    "b200_attn_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i] + [_l] * 12 + [_f, _f, _i, _i, _p, _p, _p],
+    "b200_attn_bwd": [_p] * 10 + [_i] * 7 + [_p, _f, _f, _i, _i, _p, _p, _p],
     "b200_ce_bwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _l, _p],
 }
 _RESTYPES = {"b200_last_error": c_char_p}

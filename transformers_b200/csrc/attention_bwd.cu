@@ -1,0 +1,654 @@
+// Flash attention backward on tcgen05 / TMEM / TMA for sm_100a (autograd of the reference attention core,
+// models/llama/modeling_llama.py:191-213), as two atomics-free, deterministic kernels plus a small preprocess:
+//
+//   attn_bwd_prep   delta[b,h,i] = sum_d dO*O (fp32), lse2 = lse * log2(e) (+inf for fully masked rows)
+//   attn_bwd_dkdv   one CTA per (batch, kv head, 128-row kv tile); loops over the GQA group's q heads and 64-row q tiles:
+//                     S^T = K Q^T, dP^T = V dO^T            (SS MMAs, M = kv rows, N = 64 q rows, double-buffered TMEM)
+//                     P^T = exp2(S^T c - lse2), dS^T = P^T (dP^T - delta)   (one thread per kv row; written to TMEM, bf16)
+//                     dV += P^T dO, dK += dS^T Q             (TS MMAs: A from TMEM, B = dO / Q tiles read MN-major)
+//   attn_bwd_dq     one CTA per (batch, q head, 128-row q tile); loops over 64-row kv tiles:
+//                     S = Q K^T, dP = dO V^T;  dS = P (dP - delta);  dQ += dS K   (A = dS from TMEM, B = K MN-major)
+// Recomputing S / dP in both kernels costs 7 instead of 5 MMAs per tile pair but needs no dQ atomics, no smem
+// transposes (the transposed operands are produced directly in TMEM by swapping the MMA roles) and is bit-reproducible.
+#include "attn_common.cuh"
+
+namespace b200 {
+
+constexpr int BWD_THREADS = 192;
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct AttnBwdParams {
+  AttnMask mask;
+  int B, Hq, Hkv;
+  float scale, softcap;
+  const float* lse2;   // [B, Hq, lse_stride]
+  const float* delta;  // [B, Hq, lse_stride]
+  int lse_stride;
+  __nv_bfloat16* dq;
+  __nv_bfloat16* dk;
+  __nv_bfloat16* dv;
+  int64_t dq_bs, dq_rs, dq_hs, dk_bs, dk_rs, dk_hs, dv_bs, dv_rs, dv_hs;
+};
+
+// ------------------------------------------------------------------------------------------------ preprocess
+__global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
+                                     const float* __restrict__ lse, float* __restrict__ delta, float* __restrict__ lse2,
+                                     int B, int Hq, int Sq, int D, int64_t o_bs, int64_t o_rs, int64_t o_hs,
+                                     int64_t do_bs, int64_t do_rs, int64_t do_hs, int lse_stride) {
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total = B * Hq * lse_stride;
+  if (warp_global >= total) return;
+  const int i = warp_global % lse_stride;
+  const int h = (warp_global / lse_stride) % Hq;
+  const int b = warp_global / (lse_stride * Hq);
+  float acc = 0.f;
+  if (i < Sq) {
+    const __nv_bfloat16* orow = o + b * o_bs + static_cast<int64_t>(i) * o_rs + h * o_hs;
+    const __nv_bfloat16* drow = dout + b * do_bs + static_cast<int64_t>(i) * do_rs + h * do_hs;
+    for (int c = lane * 2; c < D; c += 64) {
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(orow + c));
+      const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(drow + c));
+      acc += a.x * d.x + a.y * d.y;
+    }
+  }
+#pragma unroll
+  for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
+  if (lane == 0) {
+    delta[warp_global] = acc;
+    float l = INFINITY;
+    if (i < Sq) {
+      const float v = lse[(static_cast<size_t>(b) * Hq + h) * lse_stride + i];
+      l = (v == -INFINITY) ? INFINITY : v * kLog2e;
+    }
+    lse2[warp_global] = l;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ dK / dV
+template <int D, bool SOFTCAP>
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                     AttnBwdParams p) {
+  constexpr int DCH = D / 64;
+  constexpr int KV_TILE = 128, Q_TILE = 64;
+  constexpr int KV_BYTES = KV_TILE * D * 2;       // K or V tile
+  constexpr int KV_CHUNK = KV_TILE * 128;         // 128 rows x 64 cols
+  constexpr int Q_BYTES = Q_TILE * D * 2;         // Q or dO tile
+  constexpr int Q_CHUNK = Q_TILE * 128;           // 64 rows x 64 cols
+  constexpr uint32_t ST_COL = 0, DP_COL = 128, DV_COL = 256, DK_COL = 384;  // ST/DP: 2 buffers x 64 cols each
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + KV_BYTES;
+  uint8_t* sQ = sV + KV_BYTES;          // [2][Q_BYTES]
+  uint8_t* sdO = sQ + 2 * Q_BYTES;      // [2][Q_BYTES]
+  float* sLse = reinterpret_cast<float*>(sdO + 2 * Q_BYTES);  // [2][64]
+  float* sDelta = sLse + 2 * Q_TILE;                           // [2][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 2 * Q_TILE);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* q_full = bars + 1;    // [2]
+  uint64_t* q_empty = bars + 3;   // [2]
+  uint64_t* sdp_full = bars + 5;  // [2]  S^T / dP^T accumulators ready
+  uint64_t* pds_full = bars + 7;  // [2]  P^T / dS^T written to TMEM
+  uint64_t* acc_full = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const AttnMask& mk = p.mask;
+  const int n_rep = p.Hq / p.Hkv;
+  const int num_kv_tiles = (mk.Skv + KV_TILE - 1) / KV_TILE;
+  const int jt = blockIdx.x % num_kv_tiles;
+  const int bh = blockIdx.x / num_kv_tiles;
+  const int hkv = bh % p.Hkv;
+  const int b = bh / p.Hkv;
+  const int kv0 = jt * KV_TILE;
+  const int off = mk.Skv - mk.Sq;
+  const int kv_lo = max(mk.kv_start ? mk.kv_start[b] : 0, 0);
+  const int kv_hi = min(mk.kv_end ? mk.kv_end[b] : mk.Skv, mk.Skv);
+  // q-tile range that can attend to this kv tile
+  int q_first = 0, q_last = mk.Sq - 1;
+  if (mk.causal) q_first = max(q_first, kv0 - off);
+  if (mk.window > 0) q_last = min(q_last, kv0 + KV_TILE - 1 + mk.window - 1 - off);
+  const bool any_kv = (kv0 < kv_hi) && (kv0 + KV_TILE > kv_lo);
+  const int qt_lo = q_first / Q_TILE;
+  const int qt_hi = (any_kv && q_last >= q_first) ? q_last / Q_TILE + 1 : qt_lo;
+  const int n_qt = qt_hi - qt_lo;
+  const int n_iter = n_qt * n_rep;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmK);
+    prefetch_tmap(&tmV);
+    prefetch_tmap(&tmdO);
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&sdp_full[i], 1);
+      mbar_init(&pds_full[i], 128);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0 && n_iter > 0) {
+      mbar_expect_tx(kv_full, 2 * KV_BYTES);
+#pragma unroll
+      for (int c = 0; c < DCH; ++c) {
+        tma_load_4d(sK + c * KV_CHUNK, &tmK, kv_full, c * 64, kv0, hkv, b);
+        tma_load_4d(sV + c * KV_CHUNK, &tmV, kv_full, c * 64, kv0, hkv, b);
+      }
+      for (int it = 0; it < n_iter; ++it) {
+        const int buf = it & 1;
+        const int hq = hkv * n_rep + it / n_qt;
+        const int q0 = (qt_lo + it % n_qt) * Q_TILE;
+        mbar_wait(&q_empty[buf], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&q_full[buf], 2 * Q_BYTES + 2 * Q_TILE * 4);
+#pragma unroll
+        for (int c = 0; c < DCH; ++c) {
+          tma_load_4d(sQ + buf * Q_BYTES + c * Q_CHUNK, &tmQ, &q_full[buf], c * 64, q0, hq, b);
+          tma_load_4d(sdO + buf * Q_BYTES + c * Q_CHUNK, &tmdO, &q_full[buf], c * 64, q0, hq, b);
+        }
+        const size_t row_base = (static_cast<size_t>(b) * p.Hq + hq) * p.lse_stride + q0;
+        bulk_load_1d(sLse + buf * Q_TILE, p.lse2 + row_base, Q_TILE * 4, &q_full[buf]);
+        bulk_load_1d(sDelta + buf * Q_TILE, p.delta + row_base, Q_TILE * 4, &q_full[buf]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_iter > 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(KV_TILE, Q_TILE, 0, 0);
+      constexpr uint32_t idesc_acc = make_idesc_bf16(KV_TILE, D, 0, 1);
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), adO = smem_u32(sdO);
+      auto issue_sdp = [&](int it) {
+        const int buf = it & 1;
+        mbar_wait(&q_full[buf], (it >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t oa = (kk / 4) * KV_CHUNK + (kk % 4) * 32;
+          const uint32_t ob = buf * Q_BYTES + (kk / 4) * Q_CHUNK + (kk % 4) * 32;
+          umma_ss(tmem_base + ST_COL + buf * 64, make_smem_desc(aK + oa, 16, 1024, SWZ_128B),
+                  make_smem_desc(aQ + ob, 16, 1024, SWZ_128B), idesc_s, kk != 0);
+        }
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t oa = (kk / 4) * KV_CHUNK + (kk % 4) * 32;
+          const uint32_t ob = buf * Q_BYTES + (kk / 4) * Q_CHUNK + (kk % 4) * 32;
+          umma_ss(tmem_base + DP_COL + buf * 64, make_smem_desc(aV + oa, 16, 1024, SWZ_128B),
+                  make_smem_desc(adO + ob, 16, 1024, SWZ_128B), idesc_s, kk != 0);
+        }
+        umma_commit(&sdp_full[buf]);
+      };
+      mbar_wait(kv_full, 0);
+      issue_sdp(0);
+      for (int it = 0; it < n_iter; ++it) {
+        const int buf = it & 1;
+        if (it + 1 < n_iter) issue_sdp(it + 1);
+        mbar_wait(&pds_full[buf], (it >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < Q_TILE / 16; ++kk) {
+          // dO / Q as MN-major B: 64-col chunks Q_CHUNK apart (LBO), 8-row groups 1024 B apart (SBO), 16 rows per k-step
+          umma_ts(tmem_base + DV_COL, tmem_base + ST_COL + buf * 64 + kk * 8,
+                  make_smem_desc(adO + buf * Q_BYTES + kk * 2048, Q_CHUNK, 1024, SWZ_128B), idesc_acc, (it | kk) != 0);
+        }
+#pragma unroll
+        for (int kk = 0; kk < Q_TILE / 16; ++kk) {
+          umma_ts(tmem_base + DK_COL, tmem_base + DP_COL + buf * 64 + kk * 8,
+                  make_smem_desc(aQ + buf * Q_BYTES + kk * 2048, Q_CHUNK, 1024, SWZ_128B), idesc_acc, (it | kk) != 0);
+        }
+        umma_commit(&q_empty[buf]);
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const int kvpos = kv0 + row;
+    const uint32_t tlane = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
+    const float c2 = SOFTCAP ? p.softcap * kLog2e : p.scale * kLog2e;
+    const float pre = SOFTCAP ? p.scale / p.softcap : 1.0f;
+    const bool row_valid = kvpos >= kv_lo && kvpos < kv_hi;
+
+    for (int it = 0; it < n_iter; ++it) {
+      const int buf = it & 1;
+      const int q0 = (qt_lo + it % n_qt) * Q_TILE;
+      mbar_wait(&q_full[buf], (it >> 1) & 1);    // lse2 / delta rows landed (same barrier as Q / dO)
+      mbar_wait(&sdp_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      // block-uniform: does this (kv tile, q tile) pair need element masks?
+      const bool need_mask = (kv0 < kv_lo) || (kv0 + KV_TILE > kv_hi) || (q0 + Q_TILE > mk.Sq) ||
+                             (mk.causal && kv0 + KV_TILE - 1 > q0 + off) ||
+                             (mk.window > 0 && kv0 <= q0 + Q_TILE - 1 + off - mk.window);
+      const float* lrow = sLse + buf * Q_TILE;
+      const float* drow = sDelta + buf * Q_TILE;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t rs[32], rd[32];
+        tmem_ld_32x32b_x32(tlane + ST_COL + buf * 64 + hh * 32, rs);
+        tmem_ld_32x32b_x32(tlane + DP_COL + buf * 64 + hh * 32, rd);
+        tmem_ld_wait();
+        uint32_t pp[16], pd[16];
+#pragma unroll
+        for (int e2 = 0; e2 < 16; ++e2) {
+          float pv[2], dv[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int e = e2 * 2 + u;
+            const int col = hh * 32 + e;
+            float x = __uint_as_float(rs[e]);
+            float t = 0.f;
+            if (SOFTCAP) {
+              t = fast_tanh(x * pre);
+              x = t;
+            }
+            float pe = fast_exp2(fmaf(x, c2, -lrow[col]));
+            float de = pe * (__uint_as_float(rd[e]) - drow[col]);
+            if (SOFTCAP) de *= (1.0f - t * t);
+            if (need_mask) {
+              const int qi = q0 + col;
+              const int qpos = qi + off;
+              bool ok = row_valid && qi < mk.Sq;
+              if (mk.causal) ok = ok && kvpos <= qpos;
+              if (mk.window > 0) ok = ok && kvpos > qpos - mk.window;
+              if (!ok) pe = 0.f, de = 0.f;
+            }
+            pv[u] = pe;
+            dv[u] = de;
+          }
+          pp[e2] = pack_bf16(pv[0], pv[1]);
+          pd[e2] = pack_bf16(dv[0], dv[1]);
+        }
+        tmem_st_32x32b_x16(tlane + ST_COL + buf * 64 + hh * 16, pp);
+        tmem_st_32x32b_x16(tlane + DP_COL + buf * 64 + hh * 16, pd);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&pds_full[buf]);
+    }
+
+    if (n_iter > 0) {
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+    }
+    const bool store = kvpos < mk.Skv;
+    __nv_bfloat16* dvrow = p.dv + b * p.dv_bs + static_cast<int64_t>(kvpos) * p.dv_rs + hkv * p.dv_hs;
+    __nv_bfloat16* dkrow = p.dk + b * p.dk_bs + static_cast<int64_t>(kvpos) * p.dk_rs + hkv * p.dk_hs;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      const float mul = which == 0 ? 1.0f : p.scale;
+      __nv_bfloat16* dst = which == 0 ? dvrow : dkrow;
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t r[32];
+        if (n_iter > 0) {
+          tmem_ld_32x32b_x32(tlane + (which == 0 ? DV_COL : DK_COL) + c * 32, r);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) r[e] = 0;
+        }
+        if (store) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            uint4 o;
+            o.x = pack_bf16(__uint_as_float(r[v * 8 + 0]) * mul, __uint_as_float(r[v * 8 + 1]) * mul);
+            o.y = pack_bf16(__uint_as_float(r[v * 8 + 2]) * mul, __uint_as_float(r[v * 8 + 3]) * mul);
+            o.z = pack_bf16(__uint_as_float(r[v * 8 + 4]) * mul, __uint_as_float(r[v * 8 + 5]) * mul);
+            o.w = pack_bf16(__uint_as_float(r[v * 8 + 6]) * mul, __uint_as_float(r[v * 8 + 7]) * mul);
+            *reinterpret_cast<uint4*>(dst + c * 32 + v * 8) = o;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ dQ
+template <int D, bool SOFTCAP>
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                   AttnBwdParams p) {
+  constexpr int DCH = D / 64;
+  constexpr int Q_TILE = 128, KV_TILE = 64;
+  constexpr int Q_BYTES = Q_TILE * D * 2;
+  constexpr int Q_CHUNK = Q_TILE * 128;
+  constexpr int KV_BYTES = KV_TILE * D * 2;
+  constexpr int KV_CHUNK = KV_TILE * 128;
+  constexpr uint32_t S_COL = 0, DP_COL = 128, DQ_COL = 256;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sdO = sQ + Q_BYTES;
+  uint8_t* sK = sdO + Q_BYTES;       // [2][KV_BYTES]
+  uint8_t* sV = sK + 2 * KV_BYTES;   // [2][KV_BYTES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * KV_BYTES);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* sdp_full = bars + 5;  // [2]
+  uint64_t* ds_full = bars + 7;   // [2]
+  uint64_t* acc_full = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const AttnMask& mk = p.mask;
+  const int num_q_tiles = (mk.Sq + Q_TILE - 1) / Q_TILE;
+  const int bh_count = p.B * p.Hq;
+  const int qt = num_q_tiles - 1 - blockIdx.x / bh_count;
+  const int bh = blockIdx.x % bh_count;
+  const int b = bh / p.Hq;
+  const int h = bh % p.Hq;
+  const int hkv = h / (p.Hq / p.Hkv);
+  const int q0 = qt * Q_TILE;
+  const int off = mk.Skv - mk.Sq;
+  int lo = max(mk.kv_start ? mk.kv_start[b] : 0, 0);
+  int hi = min(mk.kv_end ? mk.kv_end[b] : mk.Skv, mk.Skv);
+  const int q_last = min(q0 + Q_TILE, mk.Sq) - 1 + off;
+  if (mk.causal) hi = min(hi, q_last + 1);
+  if (mk.window > 0) lo = max(lo, q0 + off - mk.window + 1);
+  const int t_lo = lo / KV_TILE;
+  const int t_hi = hi > lo ? (hi + KV_TILE - 1) / KV_TILE : t_lo;
+  const int n_iter = t_hi - t_lo;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmK);
+    prefetch_tmap(&tmV);
+    prefetch_tmap(&tmdO);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&sdp_full[i], 1);
+      mbar_init(&ds_full[i], 128);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0 && n_iter > 0) {
+      mbar_expect_tx(q_full, 2 * Q_BYTES);
+#pragma unroll
+      for (int c = 0; c < DCH; ++c) {
+        tma_load_4d(sQ + c * Q_CHUNK, &tmQ, q_full, c * 64, q0, h, b);
+        tma_load_4d(sdO + c * Q_CHUNK, &tmdO, q_full, c * 64, q0, h, b);
+      }
+      for (int it = 0; it < n_iter; ++it) {
+        const int buf = it & 1;
+        const int kv0 = (t_lo + it) * KV_TILE;
+        mbar_wait(&kv_empty[buf], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[buf], 2 * KV_BYTES);
+#pragma unroll
+        for (int c = 0; c < DCH; ++c) {
+          tma_load_4d(sK + buf * KV_BYTES + c * KV_CHUNK, &tmK, &kv_full[buf], c * 64, kv0, hkv, b);
+          tma_load_4d(sV + buf * KV_BYTES + c * KV_CHUNK, &tmV, &kv_full[buf], c * 64, kv0, hkv, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_iter > 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(Q_TILE, KV_TILE, 0, 0);
+      constexpr uint32_t idesc_acc = make_idesc_bf16(Q_TILE, D, 0, 1);
+      const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aK = smem_u32(sK), aV = smem_u32(sV);
+      auto issue_sdp = [&](int it) {
+        const int buf = it & 1;
+        mbar_wait(&kv_full[buf], (it >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t oa = (kk / 4) * Q_CHUNK + (kk % 4) * 32;
+          const uint32_t ob = buf * KV_BYTES + (kk / 4) * KV_CHUNK + (kk % 4) * 32;
+          umma_ss(tmem_base + S_COL + buf * 64, make_smem_desc(aQ + oa, 16, 1024, SWZ_128B),
+                  make_smem_desc(aK + ob, 16, 1024, SWZ_128B), idesc_s, kk != 0);
+        }
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t oa = (kk / 4) * Q_CHUNK + (kk % 4) * 32;
+          const uint32_t ob = buf * KV_BYTES + (kk / 4) * KV_CHUNK + (kk % 4) * 32;
+          umma_ss(tmem_base + DP_COL + buf * 64, make_smem_desc(adO + oa, 16, 1024, SWZ_128B),
+                  make_smem_desc(aV + ob, 16, 1024, SWZ_128B), idesc_s, kk != 0);
+        }
+        umma_commit(&sdp_full[buf]);
+      };
+      mbar_wait(q_full, 0);
+      issue_sdp(0);
+      for (int it = 0; it < n_iter; ++it) {
+        const int buf = it & 1;
+        if (it + 1 < n_iter) issue_sdp(it + 1);
+        mbar_wait(&ds_full[buf], (it >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < KV_TILE / 16; ++kk) {
+          umma_ts(tmem_base + DQ_COL, tmem_base + DP_COL + buf * 64 + kk * 8,
+                  make_smem_desc(aK + buf * KV_BYTES + kk * 2048, KV_CHUNK, 1024, SWZ_128B), idesc_acc, (it | kk) != 0);
+        }
+        umma_commit(&kv_empty[buf]);
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const int qrow = q0 + row;
+    const int qpos = qrow + off;
+    const uint32_t tlane = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
+    const float c2 = SOFTCAP ? p.softcap * kLog2e : p.scale * kLog2e;
+    const float pre = SOFTCAP ? p.scale / p.softcap : 1.0f;
+    float my_lse2 = INFINITY, my_delta = 0.f;
+    if (qrow < mk.Sq) {
+      const size_t idx = (static_cast<size_t>(b) * p.Hq + h) * p.lse_stride + qrow;
+      my_lse2 = p.lse2[idx];
+      my_delta = p.delta[idx];
+    }
+    int r_hi = min(mk.kv_end ? mk.kv_end[b] : mk.Skv, mk.Skv), r_lo = max(mk.kv_start ? mk.kv_start[b] : 0, 0);
+    if (mk.causal) r_hi = min(r_hi, qpos + 1);
+    if (mk.window > 0) r_lo = max(r_lo, qpos - mk.window + 1);
+
+    for (int it = 0; it < n_iter; ++it) {
+      const int buf = it & 1;
+      const int kv0 = (t_lo + it) * KV_TILE;
+      mbar_wait(&sdp_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const bool need_mask = (kv0 + KV_TILE > hi) || (kv0 < lo) || (mk.causal && kv0 + KV_TILE - 1 > q0 + off) ||
+                             (mk.window > 0 && kv0 <= q0 + Q_TILE - 1 + off - mk.window);
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t rs[32], rd[32];
+        tmem_ld_32x32b_x32(tlane + S_COL + buf * 64 + hh * 32, rs);
+        tmem_ld_32x32b_x32(tlane + DP_COL + buf * 64 + hh * 32, rd);
+        tmem_ld_wait();
+        uint32_t pd[16];
+#pragma unroll
+        for (int e2 = 0; e2 < 16; ++e2) {
+          float dv[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int e = e2 * 2 + u;
+            float x = __uint_as_float(rs[e]);
+            float t = 0.f;
+            if (SOFTCAP) {
+              t = fast_tanh(x * pre);
+              x = t;
+            }
+            const float pe = fast_exp2(fmaf(x, c2, -my_lse2));
+            float de = pe * (__uint_as_float(rd[e]) - my_delta);
+            if (SOFTCAP) de *= (1.0f - t * t);
+            if (need_mask) {
+              const int col = kv0 + hh * 32 + e;
+              if (col >= r_hi || col < r_lo) de = 0.f;
+            }
+            dv[u] = de;
+          }
+          pd[e2] = pack_bf16(dv[0], dv[1]);
+        }
+        tmem_st_32x32b_x16(tlane + DP_COL + buf * 64 + hh * 16, pd);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&ds_full[buf]);
+    }
+
+    if (n_iter > 0) {
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+    }
+    __nv_bfloat16* dst = p.dq + b * p.dq_bs + static_cast<int64_t>(qrow) * p.dq_rs + h * p.dq_hs;
+#pragma unroll
+    for (int c = 0; c < D / 32; ++c) {
+      uint32_t r[32];
+      if (n_iter > 0) {
+        tmem_ld_32x32b_x32(tlane + DQ_COL + c * 32, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) r[e] = 0;
+      }
+      if (qrow < mk.Sq) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          uint4 o;
+          o.x = pack_bf16(__uint_as_float(r[v * 8 + 0]) * p.scale, __uint_as_float(r[v * 8 + 1]) * p.scale);
+          o.y = pack_bf16(__uint_as_float(r[v * 8 + 2]) * p.scale, __uint_as_float(r[v * 8 + 3]) * p.scale);
+          o.z = pack_bf16(__uint_as_float(r[v * 8 + 4]) * p.scale, __uint_as_float(r[v * 8 + 5]) * p.scale);
+          o.w = pack_bf16(__uint_as_float(r[v * 8 + 6]) * p.scale, __uint_as_float(r[v * 8 + 7]) * p.scale);
+          *reinterpret_cast<uint4*>(dst + c * 32 + v * 8) = o;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <int D, bool SOFTCAP>
+static int launch_bwd(const CUtensorMap& tq64, const CUtensorMap& tk128, const CUtensorMap& tv128,
+                      const CUtensorMap& tdo64, const CUtensorMap& tq128, const CUtensorMap& tk64,
+                      const CUtensorMap& tv64, const CUtensorMap& tdo128, const AttnBwdParams& p, cudaStream_t stream) {
+  {
+    auto kern = attn_bwd_dkdv_kernel<D, SOFTCAP>;
+    constexpr int smem = 2 * 128 * D * 2 + 4 * 64 * D * 2 + 4 * 64 * 4 + 128 + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+      B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attr_set = true;
+    }
+    const int grid = ((p.mask.Skv + 127) / 128) * p.B * p.Hkv;
+    kern<<<grid, BWD_THREADS, smem, stream>>>(tq64, tk128, tv128, tdo64, p);
+    B200_CHECK_CUDA(cudaGetLastError());
+  }
+  {
+    auto kern = attn_bwd_dq_kernel<D, SOFTCAP>;
+    constexpr int smem = 2 * 128 * D * 2 + 4 * 64 * D * 2 + 128 + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+      B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attr_set = true;
+    }
+    const int grid = ((p.mask.Sq + 127) / 128) * p.B * p.Hq;
+    kern<<<grid, BWD_THREADS, smem, stream>>>(tq128, tk64, tv64, tdo128, p);
+    B200_CHECK_CUDA(cudaGetLastError());
+  }
+  return B200_OK;
+}
+
+}  // namespace b200
+
+// Workspace: fp32 [2 * B * Hq * lse_stride] (delta, lse2).  lse is the forward's output with the same lse_stride
+// (a multiple of 128 and >= Sq).  All tensors are strided [B, S, h, D] views (strides in elements).
+extern "C" int b200_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout,
+                             const float* lse, void* dq, void* dk, void* dv, float* workspace, int B, int Sq, int Skv,
+                             int Hq, int Hkv, int D, int lse_stride, const int64_t* strides /* 8 tensors x (bs, rs, hs):
+                             q, k, v, out, dout, dq, dk, dv */, float scale, float softcap, int causal, int window,
+                             const int* kv_start, const int* kv_end, cudaStream_t stream) {
+  using namespace b200;
+  B200_REQUIRE(D == 64 || D == 128, "attn_bwd: head_dim %d not supported (64 or 128)", D);
+  B200_REQUIRE(Hkv > 0 && Hq % Hkv == 0, "attn_bwd: Hq=%d must be a multiple of Hkv=%d", Hq, Hkv);
+  B200_REQUIRE(lse_stride >= Sq && lse_stride % 128 == 0, "attn_bwd: lse_stride %d must be >= Sq and a multiple of 128", lse_stride);
+  if (B == 0 || Sq == 0 || Skv == 0) return B200_OK;
+  const int64_t* sq = strides + 0;
+  const int64_t* sk = strides + 3;
+  const int64_t* sv = strides + 6;
+  const int64_t* so = strides + 9;
+  const int64_t* sdo = strides + 12;
+  const int64_t* sdq = strides + 15;
+  const int64_t* sdk = strides + 18;
+  const int64_t* sdv = strides + 21;
+  float* delta = workspace;
+  float* lse2 = workspace + static_cast<size_t>(B) * Hq * lse_stride;
+  {
+    const int total_warps = B * Hq * lse_stride;
+    const int threads = 256;
+    const int grid = (total_warps * 32 + threads - 1) / threads;
+    attn_bwd_prep_kernel<<<grid, threads, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), lse, delta, lse2, B,
+        Hq, Sq, D, so[0], so[1], so[2], sdo[0], sdo[1], sdo[2], lse_stride);
+    B200_CHECK_CUDA(cudaGetLastError());
+  }
+  CUtensorMap tq64, tq128, tk64, tk128, tv64, tv128, tdo64, tdo128;
+  int rc;
+  if ((rc = make_qkv_tmap(&tq64, q, D, Sq, Hq, B, sq[0], sq[1], sq[2], 64))) return rc;
+  if ((rc = make_qkv_tmap(&tq128, q, D, Sq, Hq, B, sq[0], sq[1], sq[2], 128))) return rc;
+  if ((rc = make_qkv_tmap(&tdo64, dout, D, Sq, Hq, B, sdo[0], sdo[1], sdo[2], 64))) return rc;
+  if ((rc = make_qkv_tmap(&tdo128, dout, D, Sq, Hq, B, sdo[0], sdo[1], sdo[2], 128))) return rc;
+  if ((rc = make_qkv_tmap(&tk64, k, D, Skv, Hkv, B, sk[0], sk[1], sk[2], 64))) return rc;
+  if ((rc = make_qkv_tmap(&tk128, k, D, Skv, Hkv, B, sk[0], sk[1], sk[2], 128))) return rc;
+  if ((rc = make_qkv_tmap(&tv64, v, D, Skv, Hkv, B, sv[0], sv[1], sv[2], 64))) return rc;
+  if ((rc = make_qkv_tmap(&tv128, v, D, Skv, Hkv, B, sv[0], sv[1], sv[2], 128))) return rc;
+  AttnBwdParams p;
+  p.mask.Sq = Sq;
+  p.mask.Skv = Skv;
+  p.mask.causal = causal;
+  p.mask.window = window;
+  p.mask.kv_start = kv_start;
+  p.mask.kv_end = kv_end;
+  p.B = B;
+  p.Hq = Hq;
+  p.Hkv = Hkv;
+  p.scale = scale;
+  p.softcap = softcap;
+  p.lse2 = lse2;
+  p.delta = delta;
+  p.lse_stride = lse_stride;
+  p.dq = reinterpret_cast<__nv_bfloat16*>(dq);
+  p.dk = reinterpret_cast<__nv_bfloat16*>(dk);
+  p.dv = reinterpret_cast<__nv_bfloat16*>(dv);
+  p.dq_bs = sdq[0]; p.dq_rs = sdq[1]; p.dq_hs = sdq[2];
+  p.dk_bs = sdk[0]; p.dk_rs = sdk[1]; p.dk_hs = sdk[2];
+  p.dv_bs = sdv[0]; p.dv_rs = sdv[1]; p.dv_hs = sdv[2];
+  const bool sc = softcap > 0.f;
+  if (D == 128)
+    return sc ? launch_bwd<128, true>(tq64, tk128, tv128, tdo64, tq128, tk64, tv64, tdo128, p, stream)
+              : launch_bwd<128, false>(tq64, tk128, tv128, tdo64, tq128, tk64, tv64, tdo128, p, stream);
+  return sc ? launch_bwd<64, true>(tq64, tk128, tv128, tdo64, tq128, tk64, tv64, tdo128, p, stream)
+            : launch_bwd<64, false>(tq64, tk128, tv128, tdo64, tq128, tk64, tv64, tdo128, p, stream);
+}

@@ -15,8 +15,7 @@
 //   warps 2-5 softmax:      one thread per query row: tcgen05.ld S row -> scale / softcap / mask -> online softmax with
 //                           lazy rescaling of O (only when the running max grows by > 2^8) -> P as bf16 back to TMEM
 //   epilogue (warps 2-5):   O / l -> bf16 -> global [B, Sq, Hq, D]; LSE (natural log) for the backward pass.
-#include "common.cuh"
-#include "ptx.cuh"
+#include "attn_common.cuh"
 
 namespace b200 {
 
@@ -26,7 +25,8 @@ constexpr int ATT_THREADS = 192;
 
 struct AttnFwdParams {
   __nv_bfloat16* O;
-  float* lse;  // [B, Hq, Sq]
+  float* lse;  // [B, Hq, lse_stride]
+  int lse_stride;
   int64_t o_batch_stride, o_row_stride, o_head_stride;
   int B, Hq, Hkv, Sq, Skv;
   float scale;    // softmax scaling (head_dim^-0.5)
@@ -36,17 +36,6 @@ struct AttnFwdParams {
   const int* kv_start;  // optional [B]: first valid kv index (left padding)
   const int* kv_end;    // optional [B]: one past last valid kv index (right padding)
 };
-
-__device__ __forceinline__ float fast_exp2(float x) {
-  float y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float fast_tanh(float x) {
-  float y;
-  asm volatile("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
 struct KvRange {
   int lo, hi;        // valid kv index range [lo, hi) for this (batch, q tile)
@@ -279,7 +268,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (qrow < p.Sq) {
       if (p.lse) {
         const float mc = (m_ref == -INFINITY) ? 0.f : m_ref * c2;
-        p.lse[(static_cast<size_t>(b) * p.Hq + h) * p.Sq + qrow] =
+        p.lse[(static_cast<size_t>(b) * p.Hq + h) * p.lse_stride + qrow] =
             l > 0.f ? mc * 0.6931471805599453f + logf(l) : -INFINITY;
       }
     }
@@ -316,15 +305,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
-// 4-D tensor map over strided [B, S, h, D] storage: dims {D, S, h, B}; box {64, 128, 1, 1}
-static int make_qkv_tmap(CUtensorMap* tm, const void* ptr, int D, int S, int H, int B, int64_t batch_stride,
-                         int64_t row_stride, int64_t head_stride, int box_rows) {
-  uint64_t dims[4] = {(uint64_t)D, (uint64_t)S, (uint64_t)H, (uint64_t)B};
-  uint64_t strides[4] = {1, (uint64_t)row_stride, (uint64_t)head_stride, (uint64_t)batch_stride};
-  uint32_t box[4] = {64, (uint32_t)box_rows, 1, 1};
-  return make_tmap_nd_bf16(tm, ptr, 4, dims, strides, box, true);
-}
-
 template <int D, bool SOFTCAP>
 static int launch_attn_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnFwdParams& p,
                            cudaStream_t stream) {
@@ -345,9 +325,9 @@ static int launch_attn_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const C
 }  // namespace b200
 
 // q [B, Sq, Hq, D], k/v [B, Skv, Hkv, D] and out [B, Sq, Hq, D] as strided views (strides in elements; last dim
-// contiguous).  lse: fp32 [B, Hq, Sq] or NULL.  kv_start / kv_end: optional int32 [B] valid kv ranges (padding).
-extern "C" int b200_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int Sq, int Skv,
-                             int Hq, int Hkv, int D, int64_t q_bs, int64_t q_rs, int64_t q_hs, int64_t k_bs,
+// contiguous).  lse: fp32 [B, Hq, lse_stride] or NULL (lse_stride >= Sq).  kv_start / kv_end: optional int32 [B] valid kv ranges (padding).
+extern "C" int b200_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int lse_stride, int B,
+                             int Sq, int Skv, int Hq, int Hkv, int D, int64_t q_bs, int64_t q_rs, int64_t q_hs, int64_t k_bs,
                              int64_t k_rs, int64_t k_hs, int64_t v_bs, int64_t v_rs, int64_t v_hs, int64_t o_bs,
                              int64_t o_rs, int64_t o_hs, float scale, float softcap, int causal, int window,
                              const int* kv_start, const int* kv_end, cudaStream_t stream) {
@@ -365,6 +345,7 @@ extern "C" int b200_attn_fwd(const void* q, const void* k, const void* v, void* 
   AttnFwdParams p;
   p.O = reinterpret_cast<__nv_bfloat16*>(out);
   p.lse = lse;
+  p.lse_stride = lse_stride;
   p.o_batch_stride = o_bs;
   p.o_row_stride = o_rs;
   p.o_head_stride = o_hs;

@@ -1,0 +1,220 @@
+"""torch.autograd.Function wrappers: each forward / backward is a short sequence of C-ABI kernel launches.
+
+Functions are re-entrant (no hidden global state) so the reference's GradientCheckpointingLayer
+(modeling_layers.py:49-110) can replay them.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+def _needs(ctx, i):
+    return ctx.needs_input_grad[i]
+
+
+class FusedLinearFn(torch.autograd.Function):
+    """y = x @ cat(weights)^T  -- one GEMM for several nn.Linear layers that share their input
+    (q/k/v: models/llama/modeling_llama.py:254-256; gate/up: :174-176) or a single one (o_proj, down_proj, lm_head).
+
+    ``w_fused`` is the row-wise concatenation [sum(N_i), K] (maintained by the calling module); ``weights`` are the
+    individual parameters, passed so autograd routes their gradients; gradients are row-slices of one fused wgrad."""
+
+    @staticmethod
+    def forward(ctx, x, w_fused, *weights):
+        K = x.shape[-1]
+        x2 = x.reshape(-1, K)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        y = ops.gemm(x2, w_fused)  # A = x [T,K] K-major, B = W [N,K] K-major
+        ctx.save_for_backward(x2, w_fused)
+        ctx.splits = [w.shape[0] for w in weights]
+        ctx.x_shape = x.shape
+        return y.view(*x.shape[:-1], w_fused.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w_fused = ctx.saved_tensors
+        N = w_fused.shape[0]
+        dy2 = dy.reshape(-1, N)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        dx = None
+        if _needs(ctx, 0):
+            dx = ops.gemm(dy2, w_fused, b_mn=True).view(ctx.x_shape)  # dX = dY W : B stored [K'=N, N'=K]
+        grads_w = [None] * len(ctx.splits)
+        if any(ctx.needs_input_grad[2:]):
+            dw = ops.gemm(dy2, x2, a_mn=True, b_mn=True)  # dW[N,K] = dY^T X
+            off = 0
+            for i, n in enumerate(ctx.splits):
+                if ctx.needs_input_grad[2 + i]:
+                    grads_w[i] = dw[off:off + n]
+                off += n
+        return (dx, None, *grads_w)
+
+
+class RMSNormFn(torch.autograd.Function):
+    """LlamaRMSNorm / Gemma2RMSNorm (models/llama/modeling_llama.py:62-67, models/gemma2/modeling_gemma2.py:55-63)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, eps, gemma):
+        y, rstd, _ = ops.rmsnorm_fwd(x, weight, eps, gemma)
+        ctx.save_for_backward(x, weight, rstd)
+        ctx.gemma = gemma
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, rstd = ctx.saved_tensors
+        dx, dw = ops.rmsnorm_bwd(dy, x, weight, rstd, ctx.gemma)
+        return dx if _needs(ctx, 0) else None, dw if _needs(ctx, 1) else None, None, None
+
+
+class GluFn(torch.autograd.Function):
+    """act(gate) * up on the packed [.., 2I] projection output (LlamaMLP.forward :174-176)."""
+
+    @staticmethod
+    def forward(ctx, gu, gelu):
+        ctx.save_for_backward(gu)
+        ctx.gelu = gelu
+        return ops.glu_fwd(gu, gelu)
+
+    @staticmethod
+    def backward(ctx, dh):
+        (gu,) = ctx.saved_tensors
+        return ops.glu_bwd(dh, gu, ctx.gelu), None
+
+
+class QKVRopeAttentionFn(torch.autograd.Function):
+    """Fused attention block up to (not including) o_proj, LlamaAttention.forward models/llama/modeling_llama.py:251-279:
+    packed QKV projection (one GEMM) -> RoPE in place on the private projection buffer (apply_rotary_pos_emb :138-160)
+    -> flash attention reading q/k/v as strided views of that buffer (:191-213).  Returns [B, S, Hq*D].
+    Backward: attention bwd writes dq|dk|dv straight into one packed buffer -> RoPE^T in place -> dgrad + wgrad GEMMs."""
+
+    @staticmethod
+    def forward(ctx, x, w_fused, cos, sin, cfg, kv_start, kv_end, *weights):
+        Hq, Hkv, D, scale, causal, window, softcap = cfg
+        B, S, K = x.shape
+        x2 = x.reshape(B * S, K)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        qkv = ops.gemm(x2, w_fused).view(B, S, -1)
+        ops.rope_(qkv, cos, sin, Hq + Hkv, D)
+        q = qkv[..., : Hq * D].view(B, S, Hq, D)
+        k = qkv[..., Hq * D:(Hq + Hkv) * D].view(B, S, Hkv, D)
+        v = qkv[..., (Hq + Hkv) * D:].view(B, S, Hkv, D)
+        out, lse = ops.attn_fwd(q, k, v, scale=scale, causal=causal, window=window, softcap=softcap, kv_start=kv_start,
+                                kv_end=kv_end)
+        ctx.save_for_backward(x2, w_fused, qkv, out, lse, cos, sin, kv_start, kv_end)
+        ctx.cfg = cfg
+        ctx.splits = [w.shape[0] for w in weights]
+        ctx.x_shape = x.shape
+        return out.view(B, S, Hq * D)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, w_fused, qkv, out, lse, cos, sin, kv_start, kv_end = ctx.saved_tensors
+        Hq, Hkv, D, scale, causal, window, softcap = ctx.cfg
+        B, S, W = qkv.shape
+        q = qkv[..., : Hq * D].view(B, S, Hq, D)
+        k = qkv[..., Hq * D:(Hq + Hkv) * D].view(B, S, Hkv, D)
+        v = qkv[..., (Hq + Hkv) * D:].view(B, S, Hkv, D)
+        dout4 = dout.reshape(B, S, Hq, D)
+        if not dout4.is_contiguous():
+            dout4 = dout4.contiguous()
+        dqkv = torch.empty_like(qkv)
+        dq = dqkv[..., : Hq * D].view(B, S, Hq, D)
+        dk = dqkv[..., Hq * D:(Hq + Hkv) * D].view(B, S, Hkv, D)
+        dv = dqkv[..., (Hq + Hkv) * D:].view(B, S, Hkv, D)
+        ops.attn_bwd(q, k, v, out, dout4, lse, dq, dk, dv, scale=scale, causal=causal, window=window, softcap=softcap,
+                     kv_start=kv_start, kv_end=kv_end)
+        ops.rope_(dqkv, cos, sin, Hq + Hkv, D, backward=True)
+        d2 = dqkv.view(B * S, W)
+        dx = ops.gemm(d2, w_fused, b_mn=True).view(ctx.x_shape) if _needs(ctx, 0) else None
+        grads_w = [None] * len(ctx.splits)
+        if any(ctx.needs_input_grad[7:]):
+            dw = ops.gemm(d2, x2, a_mn=True, b_mn=True)
+            off = 0
+            for i, n in enumerate(ctx.splits):
+                if ctx.needs_input_grad[7 + i]:
+                    grads_w[i] = dw[off:off + n]
+                off += n
+        return (dx, None, None, None, None, None, None, *grads_w)
+
+
+class FlashAttentionFn(torch.autograd.Function):
+    """Attention core on separate strided q/k/v views ([B, S, h, D]); used by the registry entry point
+    (AttentionInterface signature, docs/source/en/attention_interface.md:164-175) incl. the KV-cache / decode path."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, scale, causal, window, softcap, kv_start, kv_end):
+        out, lse = ops.attn_fwd(q, k, v, scale=scale, causal=causal, window=window, softcap=softcap, kv_start=kv_start,
+                                kv_end=kv_end)
+        ctx.save_for_backward(q, k, v, out, lse, kv_start, kv_end)
+        ctx.cfg = (scale, causal, window, softcap)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, out, lse, kv_start, kv_end = ctx.saved_tensors
+        scale, causal, window, softcap = ctx.cfg
+        dout = dout.contiguous()
+        dq = torch.empty(q.shape, device=q.device, dtype=q.dtype)
+        dk = torch.empty(k.shape, device=k.device, dtype=k.dtype)
+        dv = torch.empty(v.shape, device=v.device, dtype=v.dtype)
+        ops.attn_bwd(q, k, v, out, dout, lse, dq, dk, dv, scale=scale, causal=causal, window=window, softcap=softcap,
+                     kv_start=kv_start, kv_end=kv_end)
+        return dq, dk, dv, None, None, None, None, None, None
+
+
+class RopeFn(torch.autograd.Function):
+    """RoPE alone, in place on the packed buffer (used on the KV-cache path where k/v go through Cache.update)."""
+
+    @staticmethod
+    def forward(ctx, qkv, cos, sin, n_rot, D):
+        ops.rope_(qkv, cos, sin, n_rot, D)
+        ctx.mark_dirty(qkv)
+        ctx.save_for_backward(cos, sin)
+        ctx.cfg = (n_rot, D)
+        return qkv
+
+    @staticmethod
+    def backward(ctx, dqkv):
+        cos, sin = ctx.saved_tensors
+        dqkv = dqkv.contiguous().clone()
+        ops.rope_(dqkv, cos, sin, *ctx.cfg, backward=True)
+        return dqkv, None, None, None, None
+
+
+class EmbeddingFn(torch.autograd.Function):
+    """nn.Embedding gather (models/llama/modeling_llama.py:381), optional Gemma scale; backward = scatter-add."""
+
+    @staticmethod
+    def forward(ctx, ids, weight, padding_idx, scale):
+        ctx.save_for_backward(ids)
+        ctx.cfg = (weight.shape[0], padding_idx, scale)
+        return ops.embedding_fwd(ids, weight, scale)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (ids,) = ctx.saved_tensors
+        V, padding_idx, scale = ctx.cfg
+        return None, ops.embedding_bwd(ids, dout, V, padding_idx, scale), None, None
+
+
+class CausalLMLossFn(torch.autograd.Function):
+    """ForCausalLMLoss (loss/loss_utils.py:48-70): shift labels, fp32 log-softmax, mean over valid targets."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, ignore_index, num_items, shift):
+        loss, lse, denom = ops.ce_fwd(logits, labels, shift, ignore_index, num_items)
+        ctx.save_for_backward(logits, labels, lse, denom)
+        ctx.cfg = (ignore_index, shift)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        logits, labels, lse, denom = ctx.saved_tensors
+        ignore_index, shift = ctx.cfg
+        return ops.ce_bwd(logits, labels, lse, dloss, denom, shift, ignore_index), None, None, None, None

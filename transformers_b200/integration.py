@@ -1,0 +1,144 @@
+"""Registration behind the reference's own extension points:
+
+1. ``AttentionInterface.register("b200", fn)``            (utils/generic.py:1130-1132, modeling_utils.py:5092-5130)
+2. ``AttentionMaskInterface.register("b200", mask_fn)``   (masking_utils.py:711-725)
+3. ``register_patch_mapping({...})``                      (monkey_patching.py:82-154) for the Attention / MLP / RMSNorm
+   classes of Llama, Mistral and Gemma2, applied by the reference inside ``_from_config`` / ``from_pretrained``
+4. ``accelerate(model)``: the same swaps on an already-built model (``module.__class__`` assignment), plus the pieces the
+   class map cannot reach: ``nn.Embedding`` gather, ``lm_head`` GEMM and the causal-LM loss.
+
+``Trainer`` and ``generate()`` then call the model unchanged.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import functional as Fn
+from . import modules as M
+from ._lib import B200Error
+
+ATTN_NAME = M.ATTN_NAME
+_enabled = False
+
+
+# ------------------------------------------------------------------------------------------- attention registry entry
+def b200_attention_forward(module, query, key, value, attention_mask, dropout: float = 0.0, scaling: float | None = None,
+                           sliding_window: int | None = None, softcap: float | None = None, is_causal: bool | None = None,
+                           **kwargs):
+    """AttentionInterface entry (signature: docs/source/en/attention_interface.md:164-175).
+
+    query [B,Hq,Sq,D], key/value [B,Hkv,Skv,D] with arbitrary batch/head/seq strides (the reference hands us transposed
+    views of [B,S,h,D] storage, or the cat'ed KV cache) -> (attn_output [B,Sq,Hq,D], None).  GQA is resolved inside the
+    kernel (kv_head = q_head // n_rep).  The mask is never materialised: causal / sliding-window come from indices, padding
+    from the 2-D mask our AttentionMaskInterface entry forwards."""
+    if dropout:
+        raise B200Error("b200 attention: dropout is not supported")
+    if kwargs.get("s_aux") is not None:
+        raise B200Error("b200 attention: attention sinks (s_aux) are not supported")
+    if kwargs.get("cu_seq_lens_q") is not None:
+        raise B200Error("b200 attention: packed (varlen) batches are not supported yet")
+    if query.stride(-1) != 1:
+        query = query.contiguous()
+    if key.stride(-1) != 1:
+        key = key.contiguous()
+    if value.stride(-1) != 1:
+        value = value.contiguous()
+    Sq = query.shape[2]
+    if scaling is None:
+        scaling = query.shape[-1] ** -0.5
+    if is_causal is None:
+        is_causal = getattr(module, "is_causal", True)
+    # decode (q_len 1 over the whole cache) needs no causal mask (integrations/sdpa_attention.py:124)
+    causal = bool(is_causal) and Sq > 1
+    kv_start, kv_end = M.mask_to_kv_ranges(attention_mask)
+    if attention_mask is not None and attention_mask.shape[1] != key.shape[2]:
+        raise B200Error("b200 attention: padding mask length does not match the kv length")
+    q = query.transpose(1, 2)  # [B, S, h, D] views; no copies
+    k = key.transpose(1, 2)
+    v = value.transpose(1, 2)
+    out = Fn.FlashAttentionFn.apply(q, k, v, float(scaling), causal, int(sliding_window or 0), float(softcap or 0.0),
+                                    kv_start, kv_end)
+    return out, None
+
+
+def b200_attention_mask(batch_size, q_length, kv_length, q_offset=0, kv_offset=0, mask_function=None, attention_mask=None,
+                        **kwargs):
+    """AttentionMaskInterface entry: like the flash backends (masking_utils.py:607-647) return the 2-D padding mask, or
+    None when nothing is padded; causal / sliding patterns are computed inside the kernel."""
+    if attention_mask is not None:
+        attention_mask = attention_mask[:, -kv_length:]
+        if attention_mask.shape[1] == kv_length and attention_mask.all():
+            attention_mask = None
+    return attention_mask
+
+
+# -------------------------------------------------------------------------------------------------------- class maps
+def _class_map() -> dict:
+    from transformers.models.gemma2 import modeling_gemma2 as g2
+    from transformers.models.llama import modeling_llama as ll
+    from transformers.models.mistral import modeling_mistral as mi
+
+    mk = M.make_class
+    return {
+        "LlamaRMSNorm": mk(ll.LlamaRMSNorm, M.B200RMSNormMixin),
+        "LlamaMLP": mk(ll.LlamaMLP, M.B200MLPMixin),
+        "LlamaAttention": mk(ll.LlamaAttention, M.B200AttentionMixin),
+        "MistralRMSNorm": mk(mi.MistralRMSNorm, M.B200RMSNormMixin),
+        "MistralMLP": mk(mi.MistralMLP, M.B200MLPMixin),
+        "MistralAttention": mk(mi.MistralAttention, M.B200AttentionMixin),
+        "Gemma2RMSNorm": mk(g2.Gemma2RMSNorm, M.B200RMSNormMixin, _b200_gemma=True),
+        "Gemma2MLP": mk(g2.Gemma2MLP, M.B200MLPMixin),
+        "Gemma2Attention": mk(g2.Gemma2Attention, M.B200AttentionMixin),
+    }
+
+
+def enable(patch_modules: bool = True) -> None:
+    """Register the b200 backend with the reference's registries (idempotent)."""
+    global _enabled
+    from transformers import AttentionInterface, AttentionMaskInterface
+
+    AttentionInterface.register(ATTN_NAME, b200_attention_forward)
+    AttentionMaskInterface.register(ATTN_NAME, b200_attention_mask)
+    if patch_modules and not _enabled:
+        from transformers.monkey_patching import register_patch_mapping
+
+        register_patch_mapping(_class_map(), overwrite=True)
+    _enabled = True
+
+
+def b200_causal_lm_loss(logits, labels, vocab_size=None, num_items_in_batch=None, ignore_index: int = -100,
+                        shift_labels=None, **kwargs):
+    """Drop-in for ForCausalLMLoss (loss/loss_utils.py:48-70) on the fused CE kernels."""
+    if shift_labels is not None:
+        labels, shift = shift_labels, False
+    else:
+        shift = True
+    if not logits.is_cuda or logits.dtype != torch.bfloat16:
+        raise B200Error("b200 loss: expects CUDA bf16 logits")
+    if torch.is_tensor(num_items_in_batch):
+        num_items_in_batch = float(num_items_in_batch)
+    if logits.dim() == 2:
+        logits = logits.unsqueeze(0)
+        labels = labels.reshape(1, -1)
+    return Fn.CausalLMLossFn.apply(logits, labels, ignore_index, num_items_in_batch, shift)
+
+
+def accelerate(model: nn.Module, attn: bool = True, head_and_loss: bool = True) -> nn.Module:
+    """Convert an already constructed reference model in place (class swap, parameters untouched)."""
+    enable()
+    cmap = _class_map()
+    by_base = {cls.__mro__[2]: cls for cls in cmap.values()}  # (B200X, mixin, base, ...)
+    for mod in model.modules():
+        target = by_base.get(type(mod))
+        if target is not None:
+            mod.__class__ = target
+        elif type(mod) is nn.Embedding or type(mod).__name__ == "Gemma2TextScaledWordEmbedding":
+            mod.__class__ = M.make_class(type(mod), M.B200EmbeddingMixin)
+    if head_and_loss and hasattr(model, "lm_head") and type(model.lm_head) is nn.Linear and model.lm_head.bias is None:
+        model.lm_head.__class__ = M.make_class(nn.Linear, M.B200LinearMixin)
+        if getattr(model.config, "final_logit_softcapping", None) is None:
+            model.loss_function = b200_causal_lm_loss
+    if attn and hasattr(model, "set_attn_implementation"):
+        model.set_attn_implementation(ATTN_NAME)
+    return model

@@ -1,0 +1,182 @@
+"""Drop-in replacements for the reference's decoder sub-modules (Llama / Mistral / Gemma2).
+
+Each class subclasses the reference class it replaces, keeps its constructor signature, child-module names and
+parameter shapes (``q_proj/k_proj/v_proj/o_proj``, ``gate_proj/up_proj/down_proj``, ``weight``) so state dicts,
+``tp_plan`` keys and ``_can_record_outputs`` keep working, and overrides only ``forward``.
+They hold no extra constructor state, so an existing model can also be converted by swapping ``module.__class__``
+(``transformers_b200.accelerate(model)``).
+
+When ``config._attn_implementation`` is not ``"b200"`` the attention module defers to the stock reference forward, so
+``model.set_attn_implementation("eager" | "sdpa" | "b200")`` keeps switching backends (modeling_utils.py:2041-2141).
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import functional as Fn
+from ._lib import B200Error
+
+ATTN_NAME = "b200"
+
+
+# ----------------------------------------------------------------------------------------------------- weight fusion
+def fused_weight(module: nn.Module, key: str, params: list[torch.Tensor]) -> torch.Tensor:
+    """Row-wise concatenation of several [N_i, K] weights as ONE contiguous bf16 buffer, cached on the module and
+    rebuilt when any parameter is replaced or updated in place (optimizer step bumps ``_version``)."""
+    if len(params) == 1:
+        w = params[0]
+        return w if w.is_contiguous() else w.contiguous()
+    sig = tuple((p.data_ptr(), p._version, tuple(p.shape)) for p in params)
+    cache = module.__dict__.setdefault("_b200_fused", {})
+    hit = cache.get(key)
+    if hit is not None and hit[0] == sig:
+        return hit[1]
+    with torch.no_grad():
+        buf = torch.cat([p.detach() for p in params], dim=0).contiguous()
+    cache[key] = (sig, buf)
+    return buf
+
+
+def _local(p: torch.Tensor) -> torch.Tensor:
+    """Tensor-parallel parameters are DTensors whose local shard is the operand ([out/tp, in] colwise, [out, in/tp]
+    rowwise: distributed/tensor_parallel.py:161-334)."""
+    return p.to_local() if hasattr(p, "to_local") else p
+
+
+def _check_no_bias(*linears):
+    for lin in linears:
+        if getattr(lin, "bias", None) is not None:
+            raise B200Error("transformers_b200: projection biases are not supported on the fused path")
+
+
+def mask_to_kv_ranges(attention_mask: torch.Tensor | None):
+    """2-D padding mask [B, kv_len] (what our AttentionMaskInterface entry returns) -> int32 (kv_start, kv_end).
+    Padding must be contiguous on the left and/or right of each row (what tokenizers produce)."""
+    if attention_mask is None:
+        return None, None
+    if attention_mask.dim() != 2:
+        raise B200Error(f"b200 attention expects a 2-D padding mask or None, got shape {tuple(attention_mask.shape)}")
+    m = attention_mask.to(torch.bool)
+    L = m.shape[1]
+    idx = torch.arange(L, device=m.device)
+    start = torch.where(m, idx, L).amin(dim=1).to(torch.int32)
+    end = (torch.where(m, idx, -1).amax(dim=1) + 1).to(torch.int32)
+    return start.contiguous(), end.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------------------ mixins
+class B200RMSNormMixin:
+    _b200_gemma = False
+
+    def forward(self, hidden_states):  # LlamaRMSNorm.forward models/llama/modeling_llama.py:62-67
+        if not hidden_states.is_cuda:
+            return super().forward(hidden_states)
+        eps = getattr(self, "variance_epsilon", None)
+        if eps is None:
+            eps = self.eps
+        return Fn.RMSNormFn.apply(hidden_states, _local(self.weight), eps, self._b200_gemma)
+
+
+class B200MLPMixin:
+    def forward(self, x):  # LlamaMLP.forward models/llama/modeling_llama.py:174-176
+        if not x.is_cuda:
+            return super().forward(x)
+        _check_no_bias(self.gate_proj, self.up_proj, self.down_proj)
+        wg, wu, wd = _local(self.gate_proj.weight), _local(self.up_proj.weight), _local(self.down_proj.weight)
+        act = getattr(self.config, "hidden_act", None) or getattr(self.config, "hidden_activation", "silu")
+        if act not in ("silu", "gelu_pytorch_tanh"):
+            raise B200Error(f"transformers_b200: activation {act} not supported")
+        gu = Fn.FusedLinearFn.apply(x, fused_weight(self, "gate_up", [wg, wu]), wg, wu)
+        h = Fn.GluFn.apply(gu, act == "gelu_pytorch_tanh")
+        out = Fn.FusedLinearFn.apply(h, fused_weight(self, "down", [wd]), wd)
+        return _tp_allreduce(self, out)
+
+
+class B200AttentionMixin:
+    """LlamaAttention.forward models/llama/modeling_llama.py:243-281 (Mistral :141-178, Gemma2 :248-288)."""
+
+    def _b200_window(self):
+        if hasattr(self, "sliding_window"):  # Gemma2: per-layer attribute (None on full-attention layers)
+            return self.sliding_window
+        return getattr(self.config, "sliding_window", None)  # Mistral (modeling_mistral.py:172); Llama: None
+
+    def forward(self, hidden_states, position_embeddings=None, attention_mask=None, past_key_values=None, **kwargs):
+        if self.config._attn_implementation != ATTN_NAME or not hidden_states.is_cuda:
+            return super().forward(hidden_states, position_embeddings=position_embeddings, attention_mask=attention_mask,
+                                   past_key_values=past_key_values, **kwargs)
+        _check_no_bias(self.q_proj, self.k_proj, self.v_proj, self.o_proj)
+        if self.training and getattr(self, "attention_dropout", 0.0):
+            raise B200Error("transformers_b200: attention dropout is not supported")
+        wq, wk, wv, wo = (_local(self.q_proj.weight), _local(self.k_proj.weight), _local(self.v_proj.weight),
+                          _local(self.o_proj.weight))
+        D = self.head_dim
+        Hq, Hkv = wq.shape[0] // D, wk.shape[0] // D  # local head counts (module is head-count agnostic under TP)
+        B, S, _ = hidden_states.shape
+        cos, sin = position_embeddings
+        window = self._b200_window() or 0
+        softcap = getattr(self, "attn_logit_softcapping", None) or 0.0
+        wqkv = fused_weight(self, "qkv", [wq, wk, wv])
+        if past_key_values is None:
+            kv_start, kv_end = mask_to_kv_ranges(attention_mask)
+            cfg = (Hq, Hkv, D, float(self.scaling), True, int(window), float(softcap))
+            attn = Fn.QKVRopeAttentionFn.apply(hidden_states, wqkv, cos, sin, cfg, kv_start, kv_end, wq, wk, wv)
+        else:
+            from .integration import b200_attention_forward
+
+            qkv = Fn.FusedLinearFn.apply(hidden_states, wqkv, wq, wk, wv)
+            qkv = Fn.RopeFn.apply(qkv, cos, sin, Hq + Hkv, D)
+            q = qkv[..., : Hq * D].view(B, S, Hq, D).transpose(1, 2)
+            k = qkv[..., Hq * D:(Hq + Hkv) * D].view(B, S, Hkv, D).transpose(1, 2)
+            v = qkv[..., (Hq + Hkv) * D:].view(B, S, Hkv, D).transpose(1, 2)
+            k, v = past_key_values.update(k, v, self.layer_idx)
+            attn, _ = b200_attention_forward(self, q, k, v, attention_mask, dropout=0.0, scaling=self.scaling,
+                                             sliding_window=window or None, softcap=softcap or None, **kwargs)
+            attn = attn.reshape(B, S, Hq * D)
+        out = Fn.FusedLinearFn.apply(attn, fused_weight(self, "o", [wo]), wo)
+        return _tp_allreduce(self, out), None
+
+
+class B200EmbeddingMixin:
+    def forward(self, input_ids):  # nn.Embedding.forward; Gemma2TextScaledWordEmbedding models/gemma2/modeling_gemma2.py:348
+        w = _local(self.weight)
+        if not w.is_cuda:
+            return super().forward(input_ids)
+        scale = None
+        if hasattr(self, "embed_scale"):
+            scale = float(self.embed_scale.to(w.dtype))  # bf16(sqrt(hidden)) as the reference rounds it
+        return Fn.EmbeddingFn.apply(input_ids, w, self.padding_idx, scale)
+
+
+class B200LinearMixin:
+    """nn.Linear without bias on our GEMM (used for lm_head, models/llama/modeling_llama.py:480)."""
+
+    def forward(self, x):
+        w = _local(self.weight)
+        if not w.is_cuda or self.bias is not None:
+            return super().forward(x)
+        return Fn.FusedLinearFn.apply(x, fused_weight(self, "w", [w]), w)
+
+
+def _tp_allreduce(module, out):
+    group = module.__dict__.get("_b200_tp_group")
+    if group is None:
+        return out
+    from .parallel import all_reduce_sum
+
+    return all_reduce_sum(out, group)
+
+
+# --------------------------------------------------------------------------------------------------- class factories
+_CLASS_CACHE: dict = {}
+
+
+def make_class(base: type, mixin: type, **attrs) -> type:
+    """``class B200<Base>(mixin, base)`` -- created once per reference class, picklable by name lookup."""
+    key = (base, mixin, tuple(sorted(attrs.items())))
+    if key not in _CLASS_CACHE:
+        name = "B200" + base.__name__
+        cls = type(name, (mixin, base), {"__module__": __name__, "__doc__": f"{base.__name__} on B200 kernels", **attrs})
+        globals()[name] = cls
+        _CLASS_CACHE[key] = cls
+    return _CLASS_CACHE[key]

@@ -1,0 +1,275 @@
+"""Tensor-level wrappers over the C-ABI (no autograd here; see ``functional.py``).
+
+Every function takes CUDA bf16 tensors, allocates its outputs with torch (device memory + streams are the only things
+torch is used for), passes raw pointers / sizes / the current stream to ``libb200.so`` and raises on any non-zero
+return code.  There is deliberately no CPU or library fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import B200Error, check
+
+BF16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _lib_ready():
+    _lib.require_device()
+    return _lib.load()
+
+
+def _chk_bf16(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda or t.dtype != BF16:
+            raise B200Error(f"expected a CUDA bfloat16 tensor, got {t.device} {t.dtype}")
+
+
+# ----------------------------------------------------------------------------------------------------------- GEMM
+def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, out: torch.Tensor | None = None,
+         accumulate: bool = False) -> torch.Tensor:
+    """D[M,N] (+)= sum_k A(m,k) B(n,k).  ``a`` is [M,K] (or [K,M] when a_mn), ``b`` is [N,K] (or [K,N] when b_mn);
+    both 2-D with unit inner stride."""
+    lib = _lib_ready()
+    _chk_bf16(a, b, out)
+    if a.dim() != 2 or b.dim() != 2 or a.stride(1) != 1 or b.stride(1) != 1:
+        raise B200Error("gemm operands must be 2-D with unit inner stride")
+    M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
+    N, Kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
+    if K != Kb:
+        raise B200Error(f"gemm: contraction mismatch {K} vs {Kb}")
+    if out is None:
+        if accumulate:
+            raise B200Error("gemm: accumulate needs an output tensor")
+        out = torch.empty(M, N, device=a.device, dtype=BF16)
+    if out.shape != (M, N) or out.stride(1) != 1:
+        raise B200Error("gemm: bad output tensor")
+    if M == 0 or N == 0:
+        return out
+    check(lib.b200_gemm_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, a.stride(0), b.stride(0), out.stride(0),
+                             int(a_mn), int(b_mn), int(accumulate), _stream()), "b200_gemm_bf16")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------ embedding
+def embedding_fwd(ids: torch.Tensor, weight: torch.Tensor, scale: float | None = None) -> torch.Tensor:
+    lib = _lib_ready()
+    _chk_bf16(weight)
+    ids_c = ids.contiguous().view(-1)
+    if ids_c.dtype != torch.int64:
+        ids_c = ids_c.to(torch.int64)
+    T, (V, H) = ids_c.numel(), weight.shape
+    out = torch.empty(*ids.shape, H, device=weight.device, dtype=BF16)
+    err = torch.zeros(1, device=weight.device, dtype=torch.int32)
+    w = weight if weight.is_contiguous() else weight.contiguous()
+    check(lib.b200_embedding_fwd(ids_c.data_ptr(), w.data_ptr(), out.data_ptr(), T, H, V,
+                                 float(scale) if scale is not None else 1.0, int(scale is not None), err.data_ptr(), _stream()),
+          "b200_embedding_fwd")
+    return out
+
+
+def embedding_bwd(ids: torch.Tensor, dout: torch.Tensor, num_embeddings: int, padding_idx: int | None,
+                  scale: float | None = None) -> torch.Tensor:
+    lib = _lib_ready()
+    ids_c = ids.contiguous().view(-1).to(torch.int64)
+    dout = dout.contiguous()
+    H = dout.shape[-1]
+    dw = torch.zeros(num_embeddings, H, device=dout.device, dtype=BF16)
+    check(lib.b200_embedding_bwd(ids_c.data_ptr(), dout.data_ptr(), dw.data_ptr(), ids_c.numel(), H, num_embeddings,
+                                 -1 if padding_idx is None else int(padding_idx),
+                                 float(scale) if scale is not None else 1.0, int(scale is not None), _stream()),
+          "b200_embedding_bwd")
+    return dw
+
+
+# -------------------------------------------------------------------------------------------------------- RMSNorm
+def rmsnorm_fwd(x: torch.Tensor, weight: torch.Tensor, eps: float, gemma: bool = False, residual: torch.Tensor | None = None):
+    """Returns (y, rstd, residual_out).  With ``residual`` the kernel first forms r = bf16(x + residual)."""
+    lib = _lib_ready()
+    _chk_bf16(x, weight, residual)
+    H = x.shape[-1]
+    x2 = x.reshape(-1, H)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    T = x2.shape[0]
+    y = torch.empty_like(x2)
+    rstd = torch.empty(T, device=x.device, dtype=torch.float32)
+    res_out = None
+    r2 = None
+    if residual is not None:
+        r2 = residual.reshape(-1, H).contiguous()
+        res_out = torch.empty_like(x2)
+    check(lib.b200_rmsnorm_fwd(x2.data_ptr(), r2.data_ptr() if r2 is not None else None, weight.data_ptr(),
+                               res_out.data_ptr() if res_out is not None else None, y.data_ptr(), rstd.data_ptr(), T, H,
+                               float(eps), int(gemma), _stream()), "b200_rmsnorm_fwd")
+    return y.view(x.shape), rstd, (res_out.view(x.shape) if res_out is not None else None)
+
+
+def rmsnorm_bwd(dy: torch.Tensor, x: torch.Tensor, weight: torch.Tensor, rstd: torch.Tensor, gemma: bool = False):
+    lib = _lib_ready()
+    H = x.shape[-1]
+    x2 = x.reshape(-1, H)
+    dy2 = dy.reshape(-1, H)
+    if not dy2.is_contiguous():
+        dy2 = dy2.contiguous()
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    T = x2.shape[0]
+    dx = torch.empty_like(x2)
+    dw = torch.empty(H, device=x.device, dtype=BF16)
+    ws = torch.empty(lib.b200_rmsnorm_bwd_workspace_rows() * H, device=x.device, dtype=torch.float32)
+    check(lib.b200_rmsnorm_bwd(dy2.data_ptr(), x2.data_ptr(), weight.data_ptr(), rstd.data_ptr(), dx.data_ptr(),
+                               dw.data_ptr(), ws.data_ptr(), T, H, int(gemma), 0, _stream()), "b200_rmsnorm_bwd")
+    return dx.view(x.shape), dw
+
+
+# ----------------------------------------------------------------------------------------------------------- RoPE
+def rope_(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, n_rot_heads: int, head_dim: int, backward: bool = False):
+    """In place on qkv [B, S, W] (heads packed along W, the first ``n_rot_heads`` are rotated)."""
+    lib = _lib_ready()
+    _chk_bf16(qkv, cos, sin)
+    B, S, W = qkv.shape
+    if not qkv.is_contiguous():
+        raise B200Error("rope_: qkv must be contiguous")
+    cos = cos.contiguous()
+    sin = sin.contiguous()
+    cb = cos.shape[0] if cos.dim() == 3 else 1
+    if cos.shape[-2] != S or cos.shape[-1] != head_dim:
+        raise B200Error(f"rope_: cos/sin shape {tuple(cos.shape)} does not match S={S}, D={head_dim}")
+    check(lib.b200_rope(qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), B, S, n_rot_heads, head_dim, W, cb, int(backward),
+                        _stream()), "b200_rope")
+    return qkv
+
+
+# ------------------------------------------------------------------------------------------------------------ GLU
+def glu_fwd(gu: torch.Tensor, gelu: bool = False) -> torch.Tensor:
+    """gu [..., 2I] = [gate | up]  ->  act(gate) * up  [..., I]"""
+    lib = _lib_ready()
+    _chk_bf16(gu)
+    I = gu.shape[-1] // 2
+    g2 = gu.reshape(-1, 2 * I)
+    T = g2.shape[0]
+    out = torch.empty(T, I, device=gu.device, dtype=BF16)
+    check(lib.b200_glu_fwd(g2.data_ptr(), g2.data_ptr() + 2 * I, out.data_ptr(), T, I, g2.stride(0), I, int(gelu), _stream()),
+          "b200_glu_fwd")
+    return out.view(*gu.shape[:-1], I)
+
+
+def glu_bwd(dh: torch.Tensor, gu: torch.Tensor, gelu: bool = False) -> torch.Tensor:
+    lib = _lib_ready()
+    I = gu.shape[-1] // 2
+    g2 = gu.reshape(-1, 2 * I)
+    d2 = dh.reshape(-1, I)
+    if not d2.is_contiguous():
+        d2 = d2.contiguous()
+    T = g2.shape[0]
+    dgu = torch.empty(T, 2 * I, device=gu.device, dtype=BF16)
+    check(lib.b200_glu_bwd(d2.data_ptr(), g2.data_ptr(), g2.data_ptr() + 2 * I, dgu.data_ptr(), dgu.data_ptr() + 2 * I, T, I,
+                           I, g2.stride(0), 2 * I, int(gelu), _stream()), "b200_glu_bwd")
+    return dgu.view(gu.shape)
+
+
+def add(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    lib = _lib_ready()
+    _chk_bf16(a, b)
+    a = a.contiguous()
+    b = b.contiguous()
+    out = torch.empty_like(a)
+    check(lib.b200_add_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), _stream()), "b200_add_bf16")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------ attention
+def _bsh_strides(t: torch.Tensor):
+    """t is a [B, S, h, D] view with unit last stride -> (batch, row, head) strides in elements."""
+    if t.stride(3) != 1:
+        raise B200Error("attention operands need a unit stride on head_dim")
+    return t.stride(0), t.stride(1), t.stride(2)
+
+
+def _lse_stride(sq: int) -> int:
+    return (sq + 127) // 128 * 128
+
+
+def attn_fwd(q, k, v, *, scale: float, causal: bool, window: int = 0, softcap: float = 0.0, kv_start=None, kv_end=None,
+             out: torch.Tensor | None = None):
+    """q [B,Sq,Hq,D], k/v [B,Skv,Hkv,D] strided views -> (out [B,Sq,Hq,D], lse [B,Hq,lse_stride] fp32)."""
+    lib = _lib_ready()
+    _chk_bf16(q, k, v)
+    B, Sq, Hq, D = q.shape
+    Skv, Hkv = k.shape[1], k.shape[2]
+    if out is None:
+        out = torch.empty(B, Sq, Hq, D, device=q.device, dtype=BF16)
+    ls = _lse_stride(Sq)
+    lse = torch.empty(B, Hq, ls, device=q.device, dtype=torch.float32)
+    check(lib.b200_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(), ls, B, Sq, Skv, Hq, Hkv, D,
+                            *_bsh_strides(q), *_bsh_strides(k), *_bsh_strides(v), *_bsh_strides(out), float(scale),
+                            float(softcap or 0.0), int(causal), int(window or 0),
+                            kv_start.data_ptr() if kv_start is not None else None,
+                            kv_end.data_ptr() if kv_end is not None else None, _stream()), "b200_attn_fwd")
+    return out, lse
+
+
+def attn_bwd(q, k, v, out, dout, lse, dq, dk, dv, *, scale: float, causal: bool, window: int = 0, softcap: float = 0.0,
+             kv_start=None, kv_end=None):
+    """Writes dq/dk/dv (strided [B,S,h,D] views, e.g. slices of one packed buffer)."""
+    lib = _lib_ready()
+    B, Sq, Hq, D = q.shape
+    Skv, Hkv = k.shape[1], k.shape[2]
+    ls = lse.shape[-1]
+    ws = torch.empty(2 * B * Hq * ls, device=q.device, dtype=torch.float32)
+    strides = []
+    for t in (q, k, v, out, dout, dq, dk, dv):
+        strides += list(_bsh_strides(t))
+    sarr = (ctypes.c_int64 * 24)(*strides)
+    check(lib.b200_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
+                            dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), ws.data_ptr(), B, Sq, Skv, Hq, Hkv, D, ls,
+                            ctypes.cast(sarr, ctypes.c_void_p), float(scale), float(softcap or 0.0), int(causal),
+                            int(window or 0), kv_start.data_ptr() if kv_start is not None else None,
+                            kv_end.data_ptr() if kv_end is not None else None, _stream()), "b200_attn_bwd")
+    return dq, dk, dv
+
+
+# ----------------------------------------------------------------------------------------------------------- loss
+def ce_fwd(logits: torch.Tensor, labels: torch.Tensor, shift: bool = True, ignore_index: int = -100,
+           num_items: float | None = None):
+    """logits [B,S,V] bf16, labels [B,S] int64 -> (loss fp32 scalar tensor, lse [B*S], denom [1])."""
+    lib = _lib_ready()
+    _chk_bf16(logits)
+    B, S, V = logits.shape
+    lg = logits.reshape(B * S, V)
+    if not lg.is_contiguous():
+        lg = lg.contiguous()
+    labels = labels.contiguous().to(torch.int64)
+    dev = logits.device
+    lse = torch.empty(B * S, device=dev, dtype=torch.float32)
+    rows = torch.empty(B * S, device=dev, dtype=torch.float32)
+    loss = torch.empty((), device=dev, dtype=torch.float32)
+    denom = torch.empty(1, device=dev, dtype=torch.float32)
+    check(lib.b200_ce_fwd(lg.data_ptr(), labels.data_ptr(), lse.data_ptr(), rows.data_ptr(), loss.data_ptr(), denom.data_ptr(),
+                          B, S, V, lg.stride(0), int(shift), int(ignore_index), float(num_items) if num_items else 0.0, _stream()),
+          "b200_ce_fwd")
+    return loss, lse, denom
+
+
+def ce_bwd(logits: torch.Tensor, labels: torch.Tensor, lse: torch.Tensor, dloss: torch.Tensor, denom: torch.Tensor,
+           shift: bool = True, ignore_index: int = -100) -> torch.Tensor:
+    lib = _lib_ready()
+    B, S, V = logits.shape
+    lg = logits.reshape(B * S, V)
+    if not lg.is_contiguous():
+        lg = lg.contiguous()
+    labels = labels.contiguous().to(torch.int64)
+    dl = torch.empty(B * S, V, device=logits.device, dtype=BF16)
+    dloss = dloss.reshape(1).to(torch.float32).contiguous()
+    check(lib.b200_ce_bwd(lg.data_ptr(), labels.data_ptr(), lse.data_ptr(), dloss.data_ptr(), denom.data_ptr(), dl.data_ptr(), B, S,
+                          V, lg.stride(0), V, int(shift), int(ignore_index), _stream()), "b200_ce_bwd")
+    return dl.view(B, S, V)
