@@ -1,0 +1,95 @@
+"""N>1 host logic on CPU: 2 processes over gloo.  Mirrors tests/test_tensor_parallel_mixin.py:199-287 of the reference
+(TP model vs single-process model: logits, loss, per-shard gradients; fp32, atol=rtol=1e-5).
+The compute on CPU tensors is the stock reference forward (our modules defer to it off-GPU); what is under test is OUR
+sharding by the reference's tp_plan and OUR collectives (copy_to_group / all_reduce_sum / gather_last_dim)."""
+import os
+import socket
+import sys
+import traceback
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    try:
+        sys.path.insert(0, ROOT)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+        torch.set_num_threads(2)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        from _hf import import_transformers
+
+        tf = import_transformers()
+        import transformers_b200
+        from transformers_b200.parallel import resolve_plan, tensor_parallelize
+
+        transformers_b200.enable()
+        cfg = tf.LlamaConfig(vocab_size=160, hidden_size=64, intermediate_size=176, num_hidden_layers=2, num_attention_heads=4,
+                             num_key_value_heads=2, head_dim=16, max_position_embeddings=64,
+                             rope_parameters={"rope_type": "default", "rope_theta": 10000.0})
+        tf.set_seed(0)
+        model = tf.LlamaForCausalLM._from_config(cfg, attn_implementation="eager", dtype=torch.float32)
+        transformers_b200.accelerate(model, attn=False)  # swaps embedding / lm_head classes too; stays on eager (CPU)
+        model.loss_function = None
+        del model._loss_function
+        torch.manual_seed(1)
+        ids = torch.randint(0, 160, (2, 12))
+        ref = model(input_ids=ids, labels=ids)
+        ref.loss.backward()
+        ref_grads = {n: p.grad.clone() for n, p in model.named_parameters()}
+        ref_logits, ref_loss = ref.logits.detach().clone(), ref.loss.detach().clone()
+        model.zero_grad(set_to_none=True)
+
+        plan = resolve_plan(model)
+        assert plan["model.layers.*.self_attn.q_proj"] == "colwise" and plan["model.layers.*.mlp.down_proj"] == "rowwise"
+        assert plan["lm_head"] == "colwise_gather_output"
+        tensor_parallelize(model)
+        att = model.model.layers[0].self_attn
+        assert att.q_proj.weight.shape == (4 * 16 // world, 64) and att.k_proj.weight.shape == (2 * 16 // world, 64)
+        assert att.o_proj.weight.shape == (64, 4 * 16 // world)
+        assert model.model.layers[0].mlp.down_proj.weight.shape == (64, 176 // world)
+        assert model.lm_head.weight.shape == (160 // world, 64)
+        out = model(input_ids=ids, labels=ids)
+        out.loss.backward()
+        torch.testing.assert_close(out.logits, ref_logits, atol=1e-5, rtol=1e-5)
+        torch.testing.assert_close(out.loss, ref_loss, atol=1e-5, rtol=1e-5)
+        styles = {"q_proj": 0, "k_proj": 0, "v_proj": 0, "gate_proj": 0, "up_proj": 0, "lm_head": 0, "o_proj": 1, "down_proj": 1}
+        for n, p in model.named_parameters():
+            g = ref_grads[n]
+            leaf = n.split(".")[-2]
+            if leaf in styles:
+                g = g.chunk(world, dim=styles[leaf])[rank]
+            torch.testing.assert_close(p.grad, g, atol=1e-5, rtol=1e-4, msg=lambda m, n=n: f"{n}: {m}")
+        q.put((rank, "ok"))
+    except Exception:
+        q.put((rank, traceback.format_exc()))
+    finally:
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_tp2_matches_single_process_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=280) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=30)
+    for rank, msg in results:
+        assert msg == "ok", f"rank {rank}:\n{msg}"

@@ -14,7 +14,7 @@
 
 namespace b200 {
 
-constexpr int BWD_THREADS = 192;
+constexpr int BWD_THREADS = 320;  // TMA warp + MMA warp + 8 compute warps (two per TMEM lane quarter, splitting columns)
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct AttnBwdParams {
@@ -100,8 +100,10 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const AttnMask& mk = p.mask;
   const int n_rep = p.Hq / p.Hkv;
   const int num_kv_tiles = (mk.Skv + KV_TILE - 1) / KV_TILE;
-  const int jt = blockIdx.x % num_kv_tiles;
-  const int bh = blockIdx.x / num_kv_tiles;
+  // early kv tiles are attended by the most q tiles under a causal mask: schedule them first
+  const int bh_count = p.B * p.Hkv;
+  const int jt = blockIdx.x / bh_count;
+  const int bh = blockIdx.x % bh_count;
   const int hkv = bh % p.Hkv;
   const int b = bh / p.Hkv;
   const int kv0 = jt * KV_TILE;
@@ -128,7 +130,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 1);
       mbar_init(&sdp_full[i], 1);
-      mbar_init(&pds_full[i], 128);
+      mbar_init(&pds_full[i], 256);
     }
     mbar_init(acc_full, 1);
     fence_barrier_init();
@@ -212,6 +214,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
   } else {
     const int qd = warp & 3;
+    const int half = (warp - 2) >> 2;  // which 32-column half of each 64-column tile this warp owns
     const int row = qd * 32 + lane;
     const int kvpos = kv0 + row;
     const uint32_t tlane = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
@@ -231,8 +234,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                              (mk.window > 0 && kv0 <= q0 + Q_TILE - 1 + off - mk.window);
       const float* lrow = sLse + buf * Q_TILE;
       const float* drow = sDelta + buf * Q_TILE;
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
+      {
+        const int hh = half;
         uint32_t rs[32], rd[32];
         tmem_ld_32x32b_x32(tlane + ST_COL + buf * 64 + hh * 32, rs);
         tmem_ld_32x32b_x32(tlane + DP_COL + buf * 64 + hh * 32, rd);
@@ -288,7 +291,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const float mul = which == 0 ? 1.0f : p.scale;
       __nv_bfloat16* dst = which == 0 ? dvrow : dkrow;
 #pragma unroll
-      for (int c = 0; c < D / 32; ++c) {
+      for (int cc = 0; cc < D / 64; ++cc) {
+        const int c = half * (D / 64) + cc;
         uint32_t r[32];
         if (n_iter > 0) {
           tmem_ld_32x32b_x32(tlane + (which == 0 ? DV_COL : DK_COL) + c * 32, r);
@@ -379,7 +383,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
       mbar_init(&sdp_full[i], 1);
-      mbar_init(&ds_full[i], 128);
+      mbar_init(&ds_full[i], 256);
     }
     mbar_init(acc_full, 1);
     fence_barrier_init();
@@ -453,6 +457,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else {
     const int qd = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = qd * 32 + lane;
     const int qrow = q0 + row;
     const int qpos = qrow + off;
@@ -476,8 +481,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_after();
       const bool need_mask = (kv0 + KV_TILE > hi) || (kv0 < lo) || (mk.causal && kv0 + KV_TILE - 1 > q0 + off) ||
                              (mk.window > 0 && kv0 <= q0 + Q_TILE - 1 + off - mk.window);
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
+      {
+        const int hh = half;
         uint32_t rs[32], rd[32];
         tmem_ld_32x32b_x32(tlane + S_COL + buf * 64 + hh * 32, rs);
         tmem_ld_32x32b_x32(tlane + DP_COL + buf * 64 + hh * 32, rd);
@@ -519,7 +524,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     __nv_bfloat16* dst = p.dq + b * p.dq_bs + static_cast<int64_t>(qrow) * p.dq_rs + h * p.dq_hs;
 #pragma unroll
-    for (int c = 0; c < D / 32; ++c) {
+    for (int cc = 0; cc < D / 64; ++cc) {
+      const int c = half * (D / 64) + cc;
       uint32_t r[32];
       if (n_iter > 0) {
         tmem_ld_32x32b_x32(tlane + DQ_COL + c * 32, r);

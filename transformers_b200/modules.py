@@ -80,8 +80,9 @@ class B200RMSNormMixin:
 
 class B200MLPMixin:
     def forward(self, x):  # LlamaMLP.forward models/llama/modeling_llama.py:174-176
+        x = _tp_copy(self, x)
         if not x.is_cuda:
-            return super().forward(x)
+            return _tp_allreduce(self, super().forward(x))
         _check_no_bias(self.gate_proj, self.up_proj, self.down_proj)
         wg, wu, wd = _local(self.gate_proj.weight), _local(self.up_proj.weight), _local(self.down_proj.weight)
         act = getattr(self.config, "hidden_act", None) or getattr(self.config, "hidden_activation", "silu")
@@ -102,9 +103,11 @@ class B200AttentionMixin:
         return getattr(self.config, "sliding_window", None)  # Mistral (modeling_mistral.py:172); Llama: None
 
     def forward(self, hidden_states, position_embeddings=None, attention_mask=None, past_key_values=None, **kwargs):
+        hidden_states = _tp_copy(self, hidden_states)
         if self.config._attn_implementation != ATTN_NAME or not hidden_states.is_cuda:
-            return super().forward(hidden_states, position_embeddings=position_embeddings, attention_mask=attention_mask,
-                                   past_key_values=past_key_values, **kwargs)
+            out, w = super().forward(hidden_states, position_embeddings=position_embeddings, attention_mask=attention_mask,
+                                     past_key_values=past_key_values, **kwargs)
+            return _tp_allreduce(self, out), w
         _check_no_bias(self.q_proj, self.k_proj, self.v_proj, self.o_proj)
         if self.training and getattr(self, "attention_dropout", 0.0):
             raise B200Error("transformers_b200: attention dropout is not supported")
@@ -153,9 +156,27 @@ class B200LinearMixin:
 
     def forward(self, x):
         w = _local(self.weight)
+        gather = self.__dict__.get("_b200_tp_gather", False)
+        if gather:
+            x = _tp_copy(self, x)
         if not w.is_cuda or self.bias is not None:
-            return super().forward(x)
-        return Fn.FusedLinearFn.apply(x, fused_weight(self, "w", [w]), w)
+            y = super().forward(x)
+        else:
+            y = Fn.FusedLinearFn.apply(x, fused_weight(self, "w", [w]), w)
+        if gather:
+            from .parallel import gather_last_dim
+
+            y = gather_last_dim(y, self.__dict__["_b200_tp_group"])
+        return y
+
+
+def _tp_copy(module, x):
+    group = module.__dict__.get("_b200_tp_group")
+    if group is None:
+        return x
+    from .parallel import copy_to_group
+
+    return copy_to_group(x, group)
 
 
 def _tp_allreduce(module, out):

@@ -11,9 +11,31 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import B200Error, check
+from ._lib import B200Error
+from ._lib import check as _check
 
 BF16 = torch.bfloat16
+
+# kernels launched per C-ABI entry point
+_KERNELS_PER_CALL = {"b200_rmsnorm_bwd": 2, "b200_ce_fwd": 2, "b200_attn_bwd": 3}
+
+
+def check(rc: int, what: str) -> None:
+    _check(rc, what)
+    _count(_KERNELS_PER_CALL.get(what, 1))
+
+
+_LAUNCHES = 0  # kernels launched through the C-ABI by this process (bench.py reports it as gpu_launches)
+_TIMER = None  # optional callable(name) -> context manager, installed by bench.py for the per-kernel breakdown
+
+
+def launch_count() -> int:
+    return _LAUNCHES
+
+
+def _count(n: int = 1) -> None:
+    global _LAUNCHES
+    _LAUNCHES += n
 
 
 def _stream() -> int:
