@@ -224,6 +224,7 @@ def run_b200(args):
     transformers_b200.enable()
     cfg_kw = dict(LLAMA3_8B)
     cfg_kw["num_hidden_layers"] = args.layers
+    cfg_kw["use_cache"] = False  # training step: no KV cache (as Trainer does under gradient checkpointing / fwd+bwd only)
     cfg = transformers.LlamaConfig(**cfg_kw)
     transformers.set_seed(42)
     with torch.device("cuda"):

@@ -34,6 +34,8 @@ def test_gemm_layouts_vs_oracle(M, N, K):
     ref = torch.nn.functional.linear(a.float(), b.float())  # F.linear: the op behind nn.Linear (modeling_llama.py:169-171)
     for a_mn in (False, True):
         for b_mn in (False, True):
+            if (a_mn and M % 8) or (b_mn and N % 8):
+                continue  # an MN-major operand needs a 16-byte aligned row pitch
             A = (a.t().contiguous() if a_mn else a).cuda()
             B = (b.t().contiguous() if b_mn else b).cuda()
             out = ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn)

@@ -168,23 +168,41 @@ class FlashAttentionFn(torch.autograd.Function):
         return dq, dk, dv, None, None, None, None, None, None
 
 
-class RopeFn(torch.autograd.Function):
-    """RoPE alone, in place on the packed buffer (used on the KV-cache path where k/v go through Cache.update)."""
+class QKVRopeFn(torch.autograd.Function):
+    """Packed QKV projection + RoPE, returning the rotated buffer [B, S, (Hq + 2 Hkv) D] (KV-cache path: k / v then go
+    through Cache.update, models/llama/modeling_llama.py:262, and attention runs through the registry entry)."""
 
     @staticmethod
-    def forward(ctx, qkv, cos, sin, n_rot, D):
+    def forward(ctx, x, w_fused, cos, sin, n_rot, D, *weights):
+        B, S, K = x.shape
+        x2 = x.reshape(B * S, K)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        qkv = ops.gemm(x2, w_fused).view(B, S, -1)
         ops.rope_(qkv, cos, sin, n_rot, D)
-        ctx.mark_dirty(qkv)
-        ctx.save_for_backward(cos, sin)
+        ctx.save_for_backward(x2, w_fused, cos, sin)
         ctx.cfg = (n_rot, D)
+        ctx.splits = [w.shape[0] for w in weights]
+        ctx.x_shape = x.shape
         return qkv
 
     @staticmethod
     def backward(ctx, dqkv):
-        cos, sin = ctx.saved_tensors
+        x2, w_fused, cos, sin = ctx.saved_tensors
+        B, S, _ = ctx.x_shape
         dqkv = dqkv.contiguous().clone()
         ops.rope_(dqkv, cos, sin, *ctx.cfg, backward=True)
-        return dqkv, None, None, None, None
+        d2 = dqkv.view(B * S, -1)
+        dx = ops.gemm(d2, w_fused, b_mn=True).view(ctx.x_shape) if _needs(ctx, 0) else None
+        grads_w = [None] * len(ctx.splits)
+        if any(ctx.needs_input_grad[6:]):
+            dw = ops.gemm(d2, x2, a_mn=True, b_mn=True)
+            off = 0
+            for i, n in enumerate(ctx.splits):
+                if ctx.needs_input_grad[6 + i]:
+                    grads_w[i] = dw[off:off + n]
+                off += n
+        return (dx, None, None, None, None, None, *grads_w)
 
 
 class EmbeddingFn(torch.autograd.Function):

@@ -127,8 +127,7 @@ class B200AttentionMixin:
         else:
             from .integration import b200_attention_forward
 
-            qkv = Fn.FusedLinearFn.apply(hidden_states, wqkv, wq, wk, wv)
-            qkv = Fn.RopeFn.apply(qkv, cos, sin, Hq + Hkv, D)
+            qkv = Fn.QKVRopeFn.apply(hidden_states, wqkv, cos, sin, Hq + Hkv, D, wq, wk, wv)
             q = qkv[..., : Hq * D].view(B, S, Hq, D).transpose(1, 2)
             k = qkv[..., Hq * D:(Hq + Hkv) * D].view(B, S, Hkv, D).transpose(1, 2)
             v = qkv[..., (Hq + Hkv) * D:].view(B, S, Hkv, D).transpose(1, 2)

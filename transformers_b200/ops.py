@@ -62,7 +62,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     both 2-D with unit inner stride."""
     lib = _lib_ready()
     _chk_bf16(a, b, out)
-    if a.dim() != 2 or b.dim() != 2 or a.stride(1) != 1 or b.stride(1) != 1:
+    if a.dim() != 2 or b.dim() != 2 or (a.stride(1) != 1 and a.shape[1] != 1) or (b.stride(1) != 1 and b.shape[1] != 1):
         raise B200Error("gemm operands must be 2-D with unit inner stride")
     M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
     N, Kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
