@@ -214,7 +214,7 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    parallelism = args.parallelism or ("dp" if world > 1 else "none")
+    parallelism = args.parallelism or ("tp" if world > 1 else "none")  # north star: shard by the reference tp_plan
 
     import transformers
 

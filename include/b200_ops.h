@@ -27,6 +27,9 @@ const char* b200_last_error(void);     /* thread-local message of the last faili
  * D[M,N] (+)= sum_k A(m,k) B(n,k); a_mn/b_mn = 0: operand stored [M|N, K]; 1: stored [K, M|N].  tcgen05 + TMA. */
 int b200_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
                    int b_mn, int accumulate, b200_stream_t stream);
+/* CTA-pair variant (tcgen05 cta_group::2, 256x256 tile per 2-CTA cluster); b200_gemm_bf16 dispatches to it for M > 128 */
+int b200_gemm_bf16_2sm(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
+                       int b_mn, int accumulate, b200_stream_t stream);
 int b200_gemm_bf16_ex(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
                       int b_mn, int accumulate, int desc_variant, b200_stream_t stream);
 
@@ -73,6 +76,12 @@ int b200_attn_bwd(const void* q, const void* k, const void* v, const void* out, 
                   void* dq, void* dk, void* dv, float* workspace, int B, int Sq, int Skv, int Hq, int Hkv, int D,
                   int lse_stride, const int64_t* strides, float scale, float softcap, int causal, int window,
                   const int* kv_start, const int* kv_end, b200_stream_t stream);
+
+/* In-place KV-cache append replacing torch.cat in DynamicLayer.update (cache_utils.py:127-146; Cache.update :1349-1381):
+ * writes rows [offset, offset+q_len) of the preallocated [B,H,capacity,D] caches. */
+int b200_kv_append(const void* k_new, const void* v_new, void* k_cache, void* v_cache, int B, int H, int q_len, int D,
+                   int64_t ks_b, int64_t ks_h, int64_t ks_r, int64_t vs_b, int64_t vs_h, int64_t vs_r, int64_t cs_b,
+                   int64_t cs_h, int64_t cs_r, int offset, int capacity, b200_stream_t stream);
 
 /* ForCausalLMLoss (loss/loss_utils.py:32-70): shifted labels, fp32 log-sum-exp, mean over valid targets. */
 int b200_ce_fwd(const void* logits, const int64_t* labels, float* lse, float* loss_rows, float* loss_out,

@@ -241,3 +241,28 @@ def test_causal_lm_loss_vs_oracle():
     # sum / num_items_in_batch variant (loss/loss_utils.py:40-44)
     loss2, _, _ = ops.ce_fwd(logits.cuda(), labels.cuda(), num_items=17.0)
     torch.testing.assert_close(loss2.cpu(), O.causal_lm_loss(logits, labels, num_items_in_batch=17.0), atol=1e-3, rtol=1e-4)
+
+
+def test_kv_append_bit_exact_vs_reference_cat():
+    """DynamicLayer.update (cache_utils.py:127-146) semantics: returned K/V == torch.cat of everything appended so far
+    (byte copy -> bit-exact), through prefill + decode steps and one capacity growth."""
+    from transformers_b200.cache import layer_class
+
+    B, H, D = 2, 2, 64
+    layer = layer_class()()
+    layer.min_capacity = 8
+    ref_k = ref_v = None
+    g = torch.Generator().manual_seed(40)
+    for q in (5, 1, 1, 7, 1, 30):
+        # new states arrive as transposed views of [B, S, H, D] storage, exactly as the attention module produces them
+        k = torch.randn(B, q, H, D, generator=g).to(BF).cuda().transpose(1, 2)
+        v = torch.randn(B, q, H, D, generator=g).to(BF).cuda().transpose(1, 2)
+        ks, vs = layer.update(k, v)
+        ref_k = k if ref_k is None else torch.cat([ref_k, k], dim=-2)
+        ref_v = v if ref_v is None else torch.cat([ref_v, v], dim=-2)
+        assert ks.shape == ref_k.shape and torch.equal(ks, ref_k) and torch.equal(vs, ref_v)
+        assert layer.get_seq_length() == ref_k.shape[-2]
+    layer.crop(-10)
+    assert layer.get_seq_length() == ref_k.shape[-2] - 10 and torch.equal(layer.keys, ref_k[:, :, :-10])
+    layer.reset()
+    assert layer.get_seq_length() == 0

@@ -115,6 +115,25 @@ def test_generate_greedy_matches_oracle_tokens():
         assert torch.all(top - got < 5e-2), f"step {t}: chosen token is not within bf16 noise of the oracle argmax"
 
 
+def test_generate_with_inplace_kv_cache_matches_default_cache():
+    """The in-place append cache (transformers_b200.cache) is a drop-in for DynamicCache in generate()."""
+    import transformers_b200
+    from transformers_b200.cache import layer_class, make_cache
+
+    tf, cfg, model = _build("llama")
+    model = model.cuda().eval()
+    transformers_b200.accelerate(model)
+    torch.manual_seed(2)
+    ids = torch.randint(1, cfg.vocab_size, (2, 150)).cuda()
+    with torch.no_grad():
+        a = model.generate(ids, max_new_tokens=12, do_sample=False, pad_token_id=0)
+        cache = make_cache(model.config)
+        assert all(isinstance(l, layer_class()) for l in cache.layers)
+        b = model.generate(ids, max_new_tokens=12, do_sample=False, pad_token_id=0, past_key_values=cache)
+    assert torch.equal(a, b)
+    assert cache.get_seq_length() == 150 + 12 - 1
+
+
 def test_switch_back_to_sdpa_same_model():
     import transformers_b200
 

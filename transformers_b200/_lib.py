@@ -20,6 +20,7 @@ SIGNATURES = {
     "b200_device_check": [],
     "b200_last_error": [],
     "b200_gemm_bf16": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "b200_gemm_bf16_2sm": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "b200_gemm_bf16_ex": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "b200_embedding_fwd": [_p, _p, _p, _i, _i, _i, _f, _i, _p, _p],
     "b200_embedding_bwd": [_p, _p, _p, _i, _i, _i, _l, _f, _i, _p],
@@ -30,6 +31,7 @@ SIGNATURES = {
     "b200_glu_fwd": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
     "b200_glu_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "b200_add_bf16": [_p, _p, _p, _l, _p],
+    "b200_kv_append": [_p, _p, _p, _p, _i, _i, _i, _i] + [_l] * 9 + [_i, _i, _p],
     "b200_ce_fwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _l, _f, _p],
     "b200_attn_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i] + [_l] * 12 + [_f, _f, _i, _i, _p, _p, _p],
     "b200_attn_bwd": [_p] * 10 + [_i] * 7 + [_p, _f, _f, _i, _i, _p, _p, _p],

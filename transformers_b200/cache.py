@@ -1,0 +1,128 @@
+"""KV cache with in-place append behind the reference's cache protocol.
+
+``B200DynamicLayer`` subclasses the reference's ``DynamicLayer`` (cache_utils.py:113-200): same ``update`` contract
+(returns the *full* K/V to attend over, [B, Hkv, ctx, D]), same bookkeeping methods, but K/V live in a preallocated
+[B, Hkv, capacity, D] buffer that grows geometrically, and ``update`` launches one ``b200_kv_append`` kernel that writes
+only the new rows -- no O(context) ``torch.cat`` per token.  The returned tensors are strided views of the buffer; the
+b200 attention kernel reads them through strided TMA descriptors, so nothing is copied.
+
+    cache = transformers_b200.cache.make_cache(model.config)          # sliding layers keep the reference layer type
+    model.generate(ids, past_key_values=cache, ...)                   # generation/utils.py:1945-1957 accepts user caches
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+def _layer_base():
+    from transformers.cache_utils import DynamicLayer
+
+    return DynamicLayer
+
+
+def _make_layer_class():
+    DynamicLayer = _layer_base()
+
+    class B200DynamicLayer(DynamicLayer):
+        """DynamicLayer (cache_utils.py:113) with a preallocated buffer and an in-place append kernel."""
+
+        min_capacity = 256
+
+        def lazy_initialization(self, key_states, value_states):
+            self.dtype, self.device = key_states.dtype, key_states.device
+            self._len = 0
+            self._buf_k = self._buf_v = None
+            self.keys = torch.tensor([], dtype=self.dtype, device=self.device)
+            self.values = torch.tensor([], dtype=self.dtype, device=self.device)
+            self.is_initialized = True
+
+        def _reserve(self, B, H, D, need):
+            cap = 0 if self._buf_k is None else self._buf_k.shape[2]
+            if need <= cap and self._buf_k.shape[0] == B:
+                return
+            new_cap = max(self.min_capacity, cap)
+            while new_cap < need:
+                new_cap *= 2
+            nk = torch.empty(B, H, new_cap, D, dtype=self.dtype, device=self.device)
+            nv = torch.empty(B, H, new_cap, D, dtype=self.dtype, device=self.device)
+            if self._len > 0:  # amortised O(1): geometric growth
+                ops.kv_append(self._buf_k[:, :, : self._len], self._buf_v[:, :, : self._len], nk, nv, 0)
+            self._buf_k, self._buf_v = nk, nv
+
+        def update(self, key_states, value_states, *args, **kwargs):
+            if not self.is_initialized:
+                self.lazy_initialization(key_states, value_states)
+            if not key_states.is_cuda or key_states.dtype != torch.bfloat16:
+                return super().update(key_states, value_states, *args, **kwargs)
+            B, H, q, D = key_states.shape
+            self._reserve(B, H, D, self._len + q)
+            ops.kv_append(key_states, value_states, self._buf_k, self._buf_v, self._len)
+            self._len += q
+            self.keys = self._buf_k[:, :, : self._len]
+            self.values = self._buf_v[:, :, : self._len]
+            return self.keys, self.values
+
+        def get_seq_length(self) -> int:
+            return getattr(self, "_len", 0) if self.is_initialized else 0
+
+        def crop(self, tokens_to_remove: int = 0, **kw) -> None:
+            if not self.is_initialized or self._buf_k is None:
+                return
+            n = kw.get("max_length", tokens_to_remove)
+            new_len = self._len - abs(n) if n < 0 else min(self._len, n if n > 0 else self._len)
+            self._len = max(0, new_len)
+            self.keys = self._buf_k[:, :, : self._len]
+            self.values = self._buf_v[:, :, : self._len]
+
+        def reset(self) -> None:
+            if self.is_initialized:
+                self._len = 0
+                if self._buf_k is not None:
+                    self.keys = self._buf_k[:, :, :0]
+                    self.values = self._buf_v[:, :, :0]
+
+        def _rebuffer(self, k, v):
+            self._buf_k, self._buf_v = k.contiguous(), v.contiguous()
+            self.keys = self._buf_k[:, :, : self._len]
+            self.values = self._buf_v[:, :, : self._len]
+
+        def reorder_cache(self, beam_idx) -> None:
+            if self.get_seq_length() > 0:
+                self._rebuffer(self._buf_k.index_select(0, beam_idx.to(self.device)), self._buf_v.index_select(0, beam_idx.to(self.device)))
+
+        def batch_repeat_interleave(self, repeats: int) -> None:
+            if self.get_seq_length() > 0:
+                self._rebuffer(self._buf_k.repeat_interleave(repeats, dim=0), self._buf_v.repeat_interleave(repeats, dim=0))
+
+        def batch_select_indices(self, indices) -> None:
+            if self.get_seq_length() > 0:
+                self._rebuffer(self._buf_k[indices, ...], self._buf_v[indices, ...])
+
+    return B200DynamicLayer
+
+
+_LAYER_CLS = None
+
+
+def layer_class():
+    global _LAYER_CLS
+    if _LAYER_CLS is None:
+        _LAYER_CLS = _make_layer_class()
+    return _LAYER_CLS
+
+
+def make_cache(config):
+    """DynamicCache(config=...) (cache_utils.py:1773-1815) with every full-attention layer replaced by B200DynamicLayer;
+    sliding-window layers keep the reference's DynamicSlidingWindowLayer."""
+    from transformers.cache_utils import DynamicCache, DynamicLayer
+
+    cache = DynamicCache(config=config)
+    cls = layer_class()
+    n = config.get_text_config(decoder=True).num_hidden_layers
+    if len(cache.layers) == 0:
+        cache.layers = [cls() for _ in range(n)]
+    else:
+        cache.layers = [cls() if type(l) is DynamicLayer else l for l in cache.layers]
+    return cache

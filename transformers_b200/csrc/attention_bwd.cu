@@ -14,7 +14,8 @@
 
 namespace b200 {
 
-constexpr int BWD_THREADS = 320;  // TMA warp + MMA warp + 8 compute warps (two per TMEM lane quarter, splitting columns)
+constexpr int BWD_THREADS = 576;  // TMA warp + MMA warp + 16 compute warps: per TMEM lane quarter 2 column halves x 2 tile parities,
+                                  // so two consecutive tiles are in flight in the softmax/dS stage (latency-bound otherwise)
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct AttnBwdParams {
@@ -78,23 +79,24 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   constexpr int Q_BYTES = Q_TILE * D * 2;         // Q or dO tile
   constexpr int Q_CHUNK = Q_TILE * 128;           // 64 rows x 64 cols
   constexpr uint32_t ST_COL = 0, DP_COL = 128, DV_COL = 256, DK_COL = 384;  // ST/DP: 2 buffers x 64 cols each
+  constexpr int NST = 4;  // smem stages of the streamed Q / dO tiles (TMA latency ~ more than one iteration of MMAs)
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
   uint8_t* sV = sK + KV_BYTES;
-  uint8_t* sQ = sV + KV_BYTES;          // [2][Q_BYTES]
-  uint8_t* sdO = sQ + 2 * Q_BYTES;      // [2][Q_BYTES]
-  float* sLse = reinterpret_cast<float*>(sdO + 2 * Q_BYTES);  // [2][64]
-  float* sDelta = sLse + 2 * Q_TILE;                           // [2][64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 2 * Q_TILE);
+  uint8_t* sQ = sV + KV_BYTES;            // [NST][Q_BYTES]
+  uint8_t* sdO = sQ + NST * Q_BYTES;      // [NST][Q_BYTES]
+  float* sLse = reinterpret_cast<float*>(sdO + NST * Q_BYTES);  // [NST][64]
+  float* sDelta = sLse + NST * Q_TILE;                           // [NST][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + NST * Q_TILE);
   uint64_t* kv_full = bars + 0;
-  uint64_t* q_full = bars + 1;    // [2]
-  uint64_t* q_empty = bars + 3;   // [2]
-  uint64_t* sdp_full = bars + 5;  // [2]  S^T / dP^T accumulators ready
-  uint64_t* pds_full = bars + 7;  // [2]  P^T / dS^T written to TMEM
-  uint64_t* acc_full = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* q_full = bars + 1;            // [NST]
+  uint64_t* q_empty = q_full + NST;       // [NST]
+  uint64_t* sdp_full = q_empty + NST;     // [2]  S^T / dP^T accumulators ready
+  uint64_t* pds_full = sdp_full + 2;      // [2]  P^T / dS^T written to TMEM
+  uint64_t* acc_full = pds_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const AttnMask& mk = p.mask;
@@ -126,9 +128,11 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     prefetch_tmap(&tmV);
     prefetch_tmap(&tmdO);
     mbar_init(kv_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NST; ++i) {
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&sdp_full[i], 1);
       mbar_init(&pds_full[i], 256);
     }
@@ -150,19 +154,19 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tma_load_4d(sV + c * KV_CHUNK, &tmV, kv_full, c * 64, kv0, hkv, b);
       }
       for (int it = 0; it < n_iter; ++it) {
-        const int buf = it & 1;
+        const int st = it % NST;
         const int hq = hkv * n_rep + it / n_qt;
         const int q0 = (qt_lo + it % n_qt) * Q_TILE;
-        mbar_wait(&q_empty[buf], ((it >> 1) & 1) ^ 1);
-        mbar_expect_tx(&q_full[buf], 2 * Q_BYTES + 2 * Q_TILE * 4);
+        mbar_wait(&q_empty[st], ((it / NST) & 1) ^ 1);
+        mbar_expect_tx(&q_full[st], 2 * Q_BYTES + 2 * Q_TILE * 4);
 #pragma unroll
         for (int c = 0; c < DCH; ++c) {
-          tma_load_4d(sQ + buf * Q_BYTES + c * Q_CHUNK, &tmQ, &q_full[buf], c * 64, q0, hq, b);
-          tma_load_4d(sdO + buf * Q_BYTES + c * Q_CHUNK, &tmdO, &q_full[buf], c * 64, q0, hq, b);
+          tma_load_4d(sQ + st * Q_BYTES + c * Q_CHUNK, &tmQ, &q_full[st], c * 64, q0, hq, b);
+          tma_load_4d(sdO + st * Q_BYTES + c * Q_CHUNK, &tmdO, &q_full[st], c * 64, q0, hq, b);
         }
         const size_t row_base = (static_cast<size_t>(b) * p.Hq + hq) * p.lse_stride + q0;
-        bulk_load_1d(sLse + buf * Q_TILE, p.lse2 + row_base, Q_TILE * 4, &q_full[buf]);
-        bulk_load_1d(sDelta + buf * Q_TILE, p.delta + row_base, Q_TILE * 4, &q_full[buf]);
+        bulk_load_1d(sLse + st * Q_TILE, p.lse2 + row_base, Q_TILE * 4, &q_full[st]);
+        bulk_load_1d(sDelta + st * Q_TILE, p.delta + row_base, Q_TILE * 4, &q_full[st]);
       }
     }
   } else if (warp == 1) {
@@ -172,19 +176,20 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), adO = smem_u32(sdO);
       auto issue_sdp = [&](int it) {
         const int buf = it & 1;
-        mbar_wait(&q_full[buf], (it >> 1) & 1);
+        const int st = it % NST;
+        mbar_wait(&q_full[st], (it / NST) & 1);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
           const uint32_t oa = (kk / 4) * KV_CHUNK + (kk % 4) * 32;
-          const uint32_t ob = buf * Q_BYTES + (kk / 4) * Q_CHUNK + (kk % 4) * 32;
+          const uint32_t ob = st * Q_BYTES + (kk / 4) * Q_CHUNK + (kk % 4) * 32;
           umma_ss(tmem_base + ST_COL + buf * 64, make_smem_desc(aK + oa, 16, 1024, SWZ_128B),
                   make_smem_desc(aQ + ob, 16, 1024, SWZ_128B), idesc_s, kk != 0);
         }
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
           const uint32_t oa = (kk / 4) * KV_CHUNK + (kk % 4) * 32;
-          const uint32_t ob = buf * Q_BYTES + (kk / 4) * Q_CHUNK + (kk % 4) * 32;
+          const uint32_t ob = st * Q_BYTES + (kk / 4) * Q_CHUNK + (kk % 4) * 32;
           umma_ss(tmem_base + DP_COL + buf * 64, make_smem_desc(aV + oa, 16, 1024, SWZ_128B),
                   make_smem_desc(adO + ob, 16, 1024, SWZ_128B), idesc_s, kk != 0);
         }
@@ -194,27 +199,30 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       issue_sdp(0);
       for (int it = 0; it < n_iter; ++it) {
         const int buf = it & 1;
+        const int st = it % NST;
         if (it + 1 < n_iter) issue_sdp(it + 1);
         mbar_wait(&pds_full[buf], (it >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < Q_TILE / 16; ++kk) {
           // dO / Q as MN-major B: 64-col chunks Q_CHUNK apart (LBO), 8-row groups 1024 B apart (SBO), 16 rows per k-step
-          umma_ts(tmem_base + DV_COL, tmem_base + ST_COL + buf * 64 + kk * 8,
-                  make_smem_desc(adO + buf * Q_BYTES + kk * 2048, Q_CHUNK, 1024, SWZ_128B), idesc_acc, (it | kk) != 0);
+          umma_ts(tmem_base + DV_COL, tmem_base + ST_COL + buf * 64 + (kk >> 1) * 32 + (kk & 1) * 8,
+                  make_smem_desc(adO + st * Q_BYTES + kk * 2048, Q_CHUNK, 1024, SWZ_128B), idesc_acc, (it | kk) != 0);
         }
 #pragma unroll
         for (int kk = 0; kk < Q_TILE / 16; ++kk) {
-          umma_ts(tmem_base + DK_COL, tmem_base + DP_COL + buf * 64 + kk * 8,
-                  make_smem_desc(aQ + buf * Q_BYTES + kk * 2048, Q_CHUNK, 1024, SWZ_128B), idesc_acc, (it | kk) != 0);
+          umma_ts(tmem_base + DK_COL, tmem_base + DP_COL + buf * 64 + (kk >> 1) * 32 + (kk & 1) * 8,
+                  make_smem_desc(aQ + st * Q_BYTES + kk * 2048, Q_CHUNK, 1024, SWZ_128B), idesc_acc, (it | kk) != 0);
         }
-        umma_commit(&q_empty[buf]);
+        umma_commit(&q_empty[st]);
       }
       umma_commit(acc_full);
     }
   } else {
-    const int qd = warp & 3;
-    const int half = (warp - 2) >> 2;  // which 32-column half of each 64-column tile this warp owns
+    const int cw = warp - 2;
+    const int qd = warp & 3;          // TMEM lane quarter: hardware lets warp w touch lanes 32*(w%4).. only
+    const int half = (cw >> 2) & 1;   // which 32-column half of each 64-column tile this warp owns
+    const int par = cw >> 3;          // which tile parity (== TMEM buffer) this warp serves
     const int row = qd * 32 + lane;
     const int kvpos = kv0 + row;
     const uint32_t tlane = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
@@ -222,43 +230,51 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const float pre = SOFTCAP ? p.scale / p.softcap : 1.0f;
     const bool row_valid = kvpos >= kv_lo && kvpos < kv_hi;
 
-    for (int it = 0; it < n_iter; ++it) {
-      const int buf = it & 1;
+    for (int it = par; it < n_iter; it += 2) {
+      const int buf = par;
       const int q0 = (qt_lo + it % n_qt) * Q_TILE;
-      mbar_wait(&q_full[buf], (it >> 1) & 1);    // lse2 / delta rows landed (same barrier as Q / dO)
+      const int st = it % NST;
+      mbar_wait(&q_full[st], (it / NST) & 1);    // lse2 / delta rows landed (same barrier as Q / dO)
       mbar_wait(&sdp_full[buf], (it >> 1) & 1);
       tc_fence_after();
       // block-uniform: does this (kv tile, q tile) pair need element masks?
       const bool need_mask = (kv0 < kv_lo) || (kv0 + KV_TILE > kv_hi) || (q0 + Q_TILE > mk.Sq) ||
                              (mk.causal && kv0 + KV_TILE - 1 > q0 + off) ||
                              (mk.window > 0 && kv0 <= q0 + Q_TILE - 1 + off - mk.window);
-      const float* lrow = sLse + buf * Q_TILE;
-      const float* drow = sDelta + buf * Q_TILE;
-      {
-        const int hh = half;
-        uint32_t rs[32], rd[32];
-        tmem_ld_32x32b_x32(tlane + ST_COL + buf * 64 + hh * 32, rs);
-        tmem_ld_32x32b_x32(tlane + DP_COL + buf * 64 + hh * 32, rd);
-        tmem_ld_wait();
-        uint32_t pp[16], pd[16];
+      const float4* lrow4 = reinterpret_cast<const float4*>(sLse + st * Q_TILE + half * 32);
+      const float4* drow4 = reinterpret_cast<const float4*>(sDelta + st * Q_TILE + half * 32);
 #pragma unroll
-        for (int e2 = 0; e2 < 16; ++e2) {
+      for (int ch = 0; ch < 2; ++ch) {   // 16 columns at a time
+        uint32_t rs[16], rd[16];
+        const int c0 = half * 32 + ch * 16;
+        tmem_ld_32x32b_x16(tlane + ST_COL + buf * 64 + c0, rs);
+        tmem_ld_32x32b_x16(tlane + DP_COL + buf * 64 + c0, rd);
+        float lv[16], dl[16];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const float4 a = lrow4[ch * 4 + v], d4 = drow4[ch * 4 + v];
+          lv[v * 4 + 0] = a.x; lv[v * 4 + 1] = a.y; lv[v * 4 + 2] = a.z; lv[v * 4 + 3] = a.w;
+          dl[v * 4 + 0] = d4.x; dl[v * 4 + 1] = d4.y; dl[v * 4 + 2] = d4.z; dl[v * 4 + 3] = d4.w;
+        }
+        tmem_ld_wait();
+        uint32_t pp[8], pd[8];
+#pragma unroll
+        for (int e2 = 0; e2 < 8; ++e2) {
           float pv[2], dv[2];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const int e = e2 * 2 + u;
-            const int col = hh * 32 + e;
             float x = __uint_as_float(rs[e]);
             float t = 0.f;
             if (SOFTCAP) {
               t = fast_tanh(x * pre);
               x = t;
             }
-            float pe = fast_exp2(fmaf(x, c2, -lrow[col]));
-            float de = pe * (__uint_as_float(rd[e]) - drow[col]);
+            float pe = fast_exp2(fmaf(x, c2, -lv[e]));
+            float de = pe * (__uint_as_float(rd[e]) - dl[e]);
             if (SOFTCAP) de *= (1.0f - t * t);
             if (need_mask) {
-              const int qi = q0 + col;
+              const int qi = q0 + c0 + e;
               const int qpos = qi + off;
               bool ok = row_valid && qi < mk.Sq;
               if (mk.causal) ok = ok && kvpos <= qpos;
@@ -271,8 +287,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           pp[e2] = pack_bf16(pv[0], pv[1]);
           pd[e2] = pack_bf16(dv[0], dv[1]);
         }
-        tmem_st_32x32b_x16(tlane + ST_COL + buf * 64 + hh * 16, pp);
-        tmem_st_32x32b_x16(tlane + DP_COL + buf * 64 + hh * 16, pd);
+        tmem_st_32x32b_x8(tlane + ST_COL + buf * 64 + half * 32 + ch * 8, pp);  // inside this warp's own S^T columns
+        tmem_st_32x32b_x8(tlane + DP_COL + buf * 64 + half * 32 + ch * 8, pd);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -290,9 +306,9 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     for (int which = 0; which < 2; ++which) {
       const float mul = which == 0 ? 1.0f : p.scale;
       __nv_bfloat16* dst = which == 0 ? dvrow : dkrow;
-#pragma unroll
-      for (int cc = 0; cc < D / 64; ++cc) {
-        const int c = half * (D / 64) + cc;
+      {
+        const int c = half * 2 + par;   // one 32-column chunk of the D-wide accumulator per warp
+        if (c >= D / 32) continue;
         uint32_t r[32];
         if (n_iter > 0) {
           tmem_ld_32x32b_x32(tlane + (which == 0 ? DV_COL : DK_COL) + c * 32, r);
@@ -337,21 +353,22 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   constexpr int KV_BYTES = KV_TILE * D * 2;
   constexpr int KV_CHUNK = KV_TILE * 128;
   constexpr uint32_t S_COL = 0, DP_COL = 128, DQ_COL = 256;
+  constexpr int NST = 4;  // smem stages of the streamed K / V tiles
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
   uint8_t* sdO = sQ + Q_BYTES;
-  uint8_t* sK = sdO + Q_BYTES;       // [2][KV_BYTES]
-  uint8_t* sV = sK + 2 * KV_BYTES;   // [2][KV_BYTES]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * KV_BYTES);
+  uint8_t* sK = sdO + Q_BYTES;         // [NST][KV_BYTES]
+  uint8_t* sV = sK + NST * KV_BYTES;   // [NST][KV_BYTES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NST * KV_BYTES);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* sdp_full = bars + 5;  // [2]
-  uint64_t* ds_full = bars + 7;   // [2]
-  uint64_t* acc_full = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* kv_full = bars + 1;           // [NST]
+  uint64_t* kv_empty = kv_full + NST;     // [NST]
+  uint64_t* sdp_full = kv_empty + NST;    // [2]
+  uint64_t* ds_full = sdp_full + 2;       // [2]
+  uint64_t* acc_full = ds_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const AttnMask& mk = p.mask;
@@ -379,9 +396,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     prefetch_tmap(&tmV);
     prefetch_tmap(&tmdO);
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NST; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&sdp_full[i], 1);
       mbar_init(&ds_full[i], 256);
     }
@@ -403,14 +422,14 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tma_load_4d(sdO + c * Q_CHUNK, &tmdO, q_full, c * 64, q0, h, b);
       }
       for (int it = 0; it < n_iter; ++it) {
-        const int buf = it & 1;
+        const int st = it % NST;
         const int kv0 = (t_lo + it) * KV_TILE;
-        mbar_wait(&kv_empty[buf], ((it >> 1) & 1) ^ 1);
-        mbar_expect_tx(&kv_full[buf], 2 * KV_BYTES);
+        mbar_wait(&kv_empty[st], ((it / NST) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[st], 2 * KV_BYTES);
 #pragma unroll
         for (int c = 0; c < DCH; ++c) {
-          tma_load_4d(sK + buf * KV_BYTES + c * KV_CHUNK, &tmK, &kv_full[buf], c * 64, kv0, hkv, b);
-          tma_load_4d(sV + buf * KV_BYTES + c * KV_CHUNK, &tmV, &kv_full[buf], c * 64, kv0, hkv, b);
+          tma_load_4d(sK + st * KV_BYTES + c * KV_CHUNK, &tmK, &kv_full[st], c * 64, kv0, hkv, b);
+          tma_load_4d(sV + st * KV_BYTES + c * KV_CHUNK, &tmV, &kv_full[st], c * 64, kv0, hkv, b);
         }
       }
     }
@@ -421,19 +440,20 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aK = smem_u32(sK), aV = smem_u32(sV);
       auto issue_sdp = [&](int it) {
         const int buf = it & 1;
-        mbar_wait(&kv_full[buf], (it >> 1) & 1);
+        const int st = it % NST;
+        mbar_wait(&kv_full[st], (it / NST) & 1);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
           const uint32_t oa = (kk / 4) * Q_CHUNK + (kk % 4) * 32;
-          const uint32_t ob = buf * KV_BYTES + (kk / 4) * KV_CHUNK + (kk % 4) * 32;
+          const uint32_t ob = st * KV_BYTES + (kk / 4) * KV_CHUNK + (kk % 4) * 32;
           umma_ss(tmem_base + S_COL + buf * 64, make_smem_desc(aQ + oa, 16, 1024, SWZ_128B),
                   make_smem_desc(aK + ob, 16, 1024, SWZ_128B), idesc_s, kk != 0);
         }
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
           const uint32_t oa = (kk / 4) * Q_CHUNK + (kk % 4) * 32;
-          const uint32_t ob = buf * KV_BYTES + (kk / 4) * KV_CHUNK + (kk % 4) * 32;
+          const uint32_t ob = st * KV_BYTES + (kk / 4) * KV_CHUNK + (kk % 4) * 32;
           umma_ss(tmem_base + DP_COL + buf * 64, make_smem_desc(adO + oa, 16, 1024, SWZ_128B),
                   make_smem_desc(aV + ob, 16, 1024, SWZ_128B), idesc_s, kk != 0);
         }
@@ -446,18 +466,21 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (it + 1 < n_iter) issue_sdp(it + 1);
         mbar_wait(&ds_full[buf], (it >> 1) & 1);
         tc_fence_after();
+        const int st = it % NST;
 #pragma unroll
         for (int kk = 0; kk < KV_TILE / 16; ++kk) {
-          umma_ts(tmem_base + DQ_COL, tmem_base + DP_COL + buf * 64 + kk * 8,
-                  make_smem_desc(aK + buf * KV_BYTES + kk * 2048, KV_CHUNK, 1024, SWZ_128B), idesc_acc, (it | kk) != 0);
+          umma_ts(tmem_base + DQ_COL, tmem_base + DP_COL + buf * 64 + (kk >> 1) * 32 + (kk & 1) * 8,
+                  make_smem_desc(aK + st * KV_BYTES + kk * 2048, KV_CHUNK, 1024, SWZ_128B), idesc_acc, (it | kk) != 0);
         }
-        umma_commit(&kv_empty[buf]);
+        umma_commit(&kv_empty[st]);
       }
       umma_commit(acc_full);
     }
   } else {
+    const int cw = warp - 2;
     const int qd = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (cw >> 2) & 1;
+    const int par = cw >> 3;
     const int row = qd * 32 + lane;
     const int qrow = q0 + row;
     const int qpos = qrow + off;
@@ -474,22 +497,23 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (mk.causal) r_hi = min(r_hi, qpos + 1);
     if (mk.window > 0) r_lo = max(r_lo, qpos - mk.window + 1);
 
-    for (int it = 0; it < n_iter; ++it) {
-      const int buf = it & 1;
+    for (int it = par; it < n_iter; it += 2) {
+      const int buf = par;
       const int kv0 = (t_lo + it) * KV_TILE;
       mbar_wait(&sdp_full[buf], (it >> 1) & 1);
       tc_fence_after();
       const bool need_mask = (kv0 + KV_TILE > hi) || (kv0 < lo) || (mk.causal && kv0 + KV_TILE - 1 > q0 + off) ||
                              (mk.window > 0 && kv0 <= q0 + Q_TILE - 1 + off - mk.window);
-      {
-        const int hh = half;
-        uint32_t rs[32], rd[32];
-        tmem_ld_32x32b_x32(tlane + S_COL + buf * 64 + hh * 32, rs);
-        tmem_ld_32x32b_x32(tlane + DP_COL + buf * 64 + hh * 32, rd);
-        tmem_ld_wait();
-        uint32_t pd[16];
 #pragma unroll
-        for (int e2 = 0; e2 < 16; ++e2) {
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t rs[16], rd[16];
+        const int c0 = half * 32 + ch * 16;
+        tmem_ld_32x32b_x16(tlane + S_COL + buf * 64 + c0, rs);
+        tmem_ld_32x32b_x16(tlane + DP_COL + buf * 64 + c0, rd);
+        tmem_ld_wait();
+        uint32_t pd[8];
+#pragma unroll
+        for (int e2 = 0; e2 < 8; ++e2) {
           float dv[2];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
@@ -504,14 +528,14 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             float de = pe * (__uint_as_float(rd[e]) - my_delta);
             if (SOFTCAP) de *= (1.0f - t * t);
             if (need_mask) {
-              const int col = kv0 + hh * 32 + e;
+              const int col = kv0 + c0 + e;
               if (col >= r_hi || col < r_lo) de = 0.f;
             }
             dv[u] = de;
           }
           pd[e2] = pack_bf16(dv[0], dv[1]);
         }
-        tmem_st_32x32b_x16(tlane + DP_COL + buf * 64 + hh * 16, pd);
+        tmem_st_32x32b_x8(tlane + DP_COL + buf * 64 + half * 32 + ch * 8, pd);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -523,9 +547,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_after();
     }
     __nv_bfloat16* dst = p.dq + b * p.dq_bs + static_cast<int64_t>(qrow) * p.dq_rs + h * p.dq_hs;
-#pragma unroll
-    for (int cc = 0; cc < D / 64; ++cc) {
-      const int c = half * (D / 64) + cc;
+    for (int c = half * 2 + par; c < D / 32; c += 4) {   // one 32-column chunk of dQ per warp
       uint32_t r[32];
       if (n_iter > 0) {
         tmem_ld_32x32b_x32(tlane + DQ_COL + c * 32, r);
@@ -562,7 +584,7 @@ static int launch_bwd(const CUtensorMap& tq64, const CUtensorMap& tk128, const C
                       const CUtensorMap& tv64, const CUtensorMap& tdo128, const AttnBwdParams& p, cudaStream_t stream) {
   {
     auto kern = attn_bwd_dkdv_kernel<D, SOFTCAP>;
-    constexpr int smem = 2 * 128 * D * 2 + 4 * 64 * D * 2 + 4 * 64 * 4 + 128 + 1024;
+    constexpr int smem = 2 * 128 * D * 2 + 8 * 64 * D * 2 + 8 * 64 * 4 + 256 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
       B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -574,7 +596,7 @@ static int launch_bwd(const CUtensorMap& tq64, const CUtensorMap& tk128, const C
   }
   {
     auto kern = attn_bwd_dq_kernel<D, SOFTCAP>;
-    constexpr int smem = 2 * 128 * D * 2 + 4 * 64 * D * 2 + 128 + 1024;
+    constexpr int smem = 2 * 128 * D * 2 + 8 * 64 * D * 2 + 256 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
       B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

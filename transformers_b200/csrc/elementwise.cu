@@ -152,8 +152,9 @@ rmsnorm_fwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ res_in
 // ROWS at a time, reducing sum(g * xhat) per row across the block, and keeps its dW partial sums in registers.
 //   g = dy * w (Llama) or dy * (1 + w) (Gemma);  xhat = x * rstd;  dx = rstd * (g - xhat * mean(g * xhat))
 //   dw = sum_t dy * bf16(xhat) (Llama) / dy * xhat (Gemma)      -> fp32 partials [gridDim.x, H], reduced by a 2nd kernel
-template <bool GEMMA, int ROWS>
-__global__ void rmsnorm_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, const uint4* __restrict__ w,
+template <bool GEMMA, int ROWS, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1024 / MAXT)
+rmsnorm_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, const uint4* __restrict__ w,
                                    const float* __restrict__ rstd, uint4* __restrict__ dx, float* __restrict__ dw_partial,
                                    int T, int H8) {
   __shared__ float red[32][ROWS];
@@ -173,7 +174,24 @@ __global__ void rmsnorm_bwd_kernel(const uint4* __restrict__ dy, const uint4* __
   for (int e = 0; e < 8; ++e) dwacc[e] = 0.f;
   const float inv_h = 1.0f / static_cast<float>(H8 * 8);
 
+  // software pipeline: the next iteration's rows are requested before this iteration's block reduction
+  uint4 dyv[ROWS], xv[ROWS], dyn[ROWS], xn[ROWS];
+  float rsv[ROWS], rsn[ROWS];
+  auto load_rows = [&](int r0, uint4 (&dd)[ROWS], uint4 (&xx)[ROWS], float (&rr)[ROWS]) {
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const int row = r0 + r;
+      if (active && row < T) {
+        dd[r] = __ldcs(dy + static_cast<size_t>(row) * H8 + tid);
+        xx[r] = __ldcs(x + static_cast<size_t>(row) * H8 + tid);
+        rr[r] = rstd[row];
+      }
+    }
+  };
+  load_rows(blockIdx.x * ROWS, dyv, xv, rsv);
   for (int r0 = blockIdx.x * ROWS; r0 < T; r0 += gridDim.x * ROWS) {
+    const int rnext = r0 + gridDim.x * ROWS;
+    if (rnext < T) load_rows(rnext, dyn, xn, rsn);
     float g[ROWS][8], xh[ROWS][8], part[ROWS];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
@@ -181,9 +199,9 @@ __global__ void rmsnorm_bwd_kernel(const uint4* __restrict__ dy, const uint4* __
       const int row = r0 + r;
       if (active && row < T) {
         float dyf[8], xf[8];
-        unpack8(dy[static_cast<size_t>(row) * H8 + tid], dyf);
-        unpack8(x[static_cast<size_t>(row) * H8 + tid], xf);
-        const float rs = rstd[row];
+        unpack8(dyv[r], dyf);
+        unpack8(xv[r], xf);
+        const float rs = rsv[r];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           xh[r][e] = xf[e] * rs;
@@ -214,12 +232,18 @@ __global__ void rmsnorm_bwd_kernel(const uint4* __restrict__ dy, const uint4* __
     for (int r = 0; r < ROWS; ++r) {
       const int row = r0 + r;
       if (active && row < T) {
-        const float rs = rstd[row];
+        const float rs = rsv[r];
         float o[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = rs * (g[r][e] - xh[r][e] * part[r]);
         dx[static_cast<size_t>(row) * H8 + tid] = pack8(o);
       }
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      dyv[r] = dyn[r];
+      xv[r] = xn[r];
+      rsv[r] = rsn[r];
     }
   }
   if (active) {
@@ -302,40 +326,79 @@ __device__ __forceinline__ float act_grad(float g, int gelu) {
   return 0.5f * (1.0f + t) + 0.5f * g * (1.0f - t * t) * k0 * (1.0f + 3.0f * k1 * g * g);
 }
 
-__global__ void glu_fwd_kernel(const __nv_bfloat16* __restrict__ gate, const __nv_bfloat16* __restrict__ up,
-                               __nv_bfloat16* __restrict__ out, int T, int I8, int ld_gu, int ld_out, int gelu) {
-  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= static_cast<size_t>(T) * I8) return;
-  const int c = idx % I8;
-  const size_t t = idx / I8;
-  float g[8], u[8], o[8];
-  unpack8(*(reinterpret_cast<const uint4*>(gate + t * ld_gu) + c), g);
-  unpack8(*(reinterpret_cast<const uint4*>(up + t * ld_gu) + c), u);
+constexpr int EW_UNROLL = 4;  // independent 16-byte chunks per thread (loads issued before any use)
+
+__global__ void __launch_bounds__(256)
+glu_fwd_kernel(const __nv_bfloat16* __restrict__ gate, const __nv_bfloat16* __restrict__ up,
+               __nv_bfloat16* __restrict__ out, int T, int I8, int ld_gu, int ld_out, int gelu) {
+  const size_t total = static_cast<size_t>(T) * I8;
+  const size_t base = static_cast<size_t>(blockIdx.x) * (blockDim.x * EW_UNROLL) + threadIdx.x;
+  uint4 gv[EW_UNROLL], uv[EW_UNROLL];
+  size_t tt[EW_UNROLL];
+  int cc[EW_UNROLL];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) o[e] = bf16_round(act_fwd(g[e], gelu)) * u[e];
-  *(reinterpret_cast<uint4*>(out + t * ld_out) + c) = pack8(o);
+  for (int j = 0; j < EW_UNROLL; ++j) {
+    const size_t idx = base + static_cast<size_t>(j) * blockDim.x;
+    if (idx < total) {
+      cc[j] = idx % I8;
+      tt[j] = idx / I8;
+      gv[j] = __ldcs(reinterpret_cast<const uint4*>(gate + tt[j] * ld_gu) + cc[j]);
+      uv[j] = __ldcs(reinterpret_cast<const uint4*>(up + tt[j] * ld_gu) + cc[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < EW_UNROLL; ++j) {
+    const size_t idx = base + static_cast<size_t>(j) * blockDim.x;
+    if (idx < total) {
+      float g[8], u[8], o[8];
+      unpack8(gv[j], g);
+      unpack8(uv[j], u);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = bf16_round(act_fwd(g[e], gelu)) * u[e];
+      *(reinterpret_cast<uint4*>(out + tt[j] * ld_out) + cc[j]) = pack8(o);
+    }
+  }
 }
 
-// dgate, dup written to dgu (same layout as gate/up); optionally re-materialises h (act_out) for the down_proj wgrad.
-__global__ void glu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ gate,
-                               const __nv_bfloat16* __restrict__ up, __nv_bfloat16* __restrict__ dgate,
-                               __nv_bfloat16* __restrict__ dup, int T, int I8, int ld_dh, int ld_gu, int ld_dgu,
-                               int gelu) {
-  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= static_cast<size_t>(T) * I8) return;
-  const int c = idx % I8;
-  const size_t t = idx / I8;
-  float d[8], g[8], u[8], dg[8], du[8];
-  unpack8(*(reinterpret_cast<const uint4*>(dh + t * ld_dh) + c), d);
-  unpack8(*(reinterpret_cast<const uint4*>(gate + t * ld_gu) + c), g);
-  unpack8(*(reinterpret_cast<const uint4*>(up + t * ld_gu) + c), u);
+constexpr int GLU_BWD_UNROLL = 2;  // 5 streams per chunk: fewer chunks per thread keeps 4 blocks/SM resident
+// dgate, dup written to dgu (same layout as gate/up).
+__global__ void __launch_bounds__(256)
+glu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ gate,
+               const __nv_bfloat16* __restrict__ up, __nv_bfloat16* __restrict__ dgate,
+               __nv_bfloat16* __restrict__ dup, int T, int I8, int ld_dh, int ld_gu, int ld_dgu, int gelu) {
+  const size_t total = static_cast<size_t>(T) * I8;
+  const size_t base = static_cast<size_t>(blockIdx.x) * (blockDim.x * GLU_BWD_UNROLL) + threadIdx.x;
+  uint4 dv[GLU_BWD_UNROLL], gv[GLU_BWD_UNROLL], uv[GLU_BWD_UNROLL];
+  size_t tt[GLU_BWD_UNROLL];
+  int cc[GLU_BWD_UNROLL];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    du[e] = d[e] * bf16_round(act_fwd(g[e], gelu));
-    dg[e] = bf16_round(d[e] * u[e]) * act_grad(g[e], gelu);
+  for (int j = 0; j < GLU_BWD_UNROLL; ++j) {
+    const size_t idx = base + static_cast<size_t>(j) * blockDim.x;
+    if (idx < total) {
+      cc[j] = idx % I8;
+      tt[j] = idx / I8;
+      dv[j] = __ldcs(reinterpret_cast<const uint4*>(dh + tt[j] * ld_dh) + cc[j]);
+      gv[j] = __ldcs(reinterpret_cast<const uint4*>(gate + tt[j] * ld_gu) + cc[j]);
+      uv[j] = __ldcs(reinterpret_cast<const uint4*>(up + tt[j] * ld_gu) + cc[j]);
+    }
   }
-  *(reinterpret_cast<uint4*>(dgate + t * ld_dgu) + c) = pack8(dg);
-  *(reinterpret_cast<uint4*>(dup + t * ld_dgu) + c) = pack8(du);
+#pragma unroll
+  for (int j = 0; j < GLU_BWD_UNROLL; ++j) {
+    const size_t idx = base + static_cast<size_t>(j) * blockDim.x;
+    if (idx < total) {
+      float d[8], g[8], u[8], dg[8], du[8];
+      unpack8(dv[j], d);
+      unpack8(gv[j], g);
+      unpack8(uv[j], u);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        du[e] = d[e] * bf16_round(act_fwd(g[e], gelu));
+        dg[e] = bf16_round(d[e] * u[e]) * act_grad(g[e], gelu);
+      }
+      *(reinterpret_cast<uint4*>(dgate + tt[j] * ld_dgu) + cc[j]) = pack8(dg);
+      *(reinterpret_cast<uint4*>(dup + tt[j] * ld_dgu) + cc[j]) = pack8(du);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ residual add
@@ -561,18 +624,20 @@ extern "C" int b200_rmsnorm_bwd(const void* dy, const void* x, const void* weigh
                                 cudaStream_t stream) {
   B200_REQUIRE(H > 0 && H % 8 == 0 && H <= 8192, "rmsnorm_bwd: H=%d must be a multiple of 8 and <= 8192", H);
   if (T == 0) return B200_OK;
-  constexpr int ROWS = 2;
+  constexpr int ROWS = 1;
   const int threads = ((H / 8 + 31) / 32) * 32;
   int grid = b200_rmsnorm_bwd_workspace_rows();
   if (grid > ceil_div(T, ROWS)) grid = ceil_div(T, ROWS);
   const uint4 *dyp = reinterpret_cast<const uint4*>(dy), *xp = reinterpret_cast<const uint4*>(x),
               *wp = reinterpret_cast<const uint4*>(weight);
-  if (gemma)
-    rmsnorm_bwd_kernel<true, ROWS><<<grid, threads, 0, stream>>>(dyp, xp, wp, rstd, reinterpret_cast<uint4*>(dx),
-                                                                 workspace, T, H / 8);
-  else
-    rmsnorm_bwd_kernel<false, ROWS><<<grid, threads, 0, stream>>>(dyp, xp, wp, rstd, reinterpret_cast<uint4*>(dx),
-                                                                  workspace, T, H / 8);
+  uint4* dxp = reinterpret_cast<uint4*>(dx);
+  if (threads <= 512) {
+    if (gemma) rmsnorm_bwd_kernel<true, ROWS, 512><<<grid, threads, 0, stream>>>(dyp, xp, wp, rstd, dxp, workspace, T, H / 8);
+    else rmsnorm_bwd_kernel<false, ROWS, 512><<<grid, threads, 0, stream>>>(dyp, xp, wp, rstd, dxp, workspace, T, H / 8);
+  } else {
+    if (gemma) rmsnorm_bwd_kernel<true, ROWS, 1024><<<grid, threads, 0, stream>>>(dyp, xp, wp, rstd, dxp, workspace, T, H / 8);
+    else rmsnorm_bwd_kernel<false, ROWS, 1024><<<grid, threads, 0, stream>>>(dyp, xp, wp, rstd, dxp, workspace, T, H / 8);
+  }
   B200_CHECK_CUDA(cudaGetLastError());
   reduce_partials_kernel<<<ceil_div(H, 256), 256, 0, stream>>>(workspace, reinterpret_cast<__nv_bfloat16*>(dweight),
                                                                grid, H, accumulate_dw);
@@ -606,7 +671,7 @@ extern "C" int b200_glu_fwd(const void* gate, const void* up, void* out, int T, 
   B200_REQUIRE(I % 8 == 0 && ld_gu % 8 == 0 && ld_out % 8 == 0, "glu_fwd: I=%d must be a multiple of 8", I);
   const size_t total = static_cast<size_t>(T) * (I / 8);
   if (total == 0) return B200_OK;
-  glu_fwd_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(
+  glu_fwd_kernel<<<ceil_div(total, 256 * EW_UNROLL), 256, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(gate), reinterpret_cast<const __nv_bfloat16*>(up),
       reinterpret_cast<__nv_bfloat16*>(out), T, I / 8, ld_gu, ld_out, gelu);
   B200_CHECK_CUDA(cudaGetLastError());
@@ -618,7 +683,7 @@ extern "C" int b200_glu_bwd(const void* dh, const void* gate, const void* up, vo
   B200_REQUIRE(I % 8 == 0 && ld_gu % 8 == 0 && ld_dh % 8 == 0 && ld_dgu % 8 == 0, "glu_bwd: I=%d must be a multiple of 8", I);
   const size_t total = static_cast<size_t>(T) * (I / 8);
   if (total == 0) return B200_OK;
-  glu_bwd_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(
+  glu_bwd_kernel<<<ceil_div(total, 256 * GLU_BWD_UNROLL), 256, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(dh), reinterpret_cast<const __nv_bfloat16*>(gate),
       reinterpret_cast<const __nv_bfloat16*>(up), reinterpret_cast<__nv_bfloat16*>(dgate),
       reinterpret_cast<__nv_bfloat16*>(dup), T, I / 8, ld_dh, ld_gu, ld_dgu, gelu);

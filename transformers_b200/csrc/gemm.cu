@@ -17,6 +17,8 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
 namespace b200 {
 
 constexpr int BM = 128;
@@ -290,7 +292,18 @@ extern "C" int b200_gemm_bf16_ex(const void* A, const void* B, void* C, int M, i
   return launch_gemm<1, 0>(tmA, tmB, p, stream);
 }
 
+extern "C" int b200_gemm_bf16_2sm(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
+                                  int a_mn, int b_mn, int accumulate, cudaStream_t stream);
+
+// Dispatcher: CTA-pair kernel (gemm2.cu, 256x256 tiles) for anything taller than one 128-row tile, else the 1-CTA kernel.
+// B200_GEMM_1SM=1 forces the 1-CTA kernel (A/B timing).
 extern "C" int b200_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
                               int a_mn, int b_mn, int accumulate, cudaStream_t stream) {
+  static const int force_1sm = [] {
+    const char* e = getenv("B200_GEMM_1SM");
+    return (e && e[0] == '1') ? 1 : 0;
+  }();
+  if (!force_1sm && M > 128 && N > 64)
+    return b200_gemm_bf16_2sm(A, B, C, M, N, K, lda, ldb, ldc, a_mn, b_mn, accumulate, stream);
   return b200_gemm_bf16_ex(A, B, C, M, N, K, lda, ldb, ldc, a_mn, b_mn, accumulate, 0, stream);
 }

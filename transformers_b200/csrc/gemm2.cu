@@ -1,0 +1,290 @@
+// bf16 GEMM on CTA pairs (tcgen05 cta_group::2): one 256x256 output tile per 2-CTA cluster.
+//
+// Same math / operand layouts / epilogue as gemm.cu (D[M,N] (+)= sum_k A(m,k) B(n,k), K- or MN-major operands), but the
+// two CTAs of a cluster (same TPC) cooperate on UMMA_M = 256: each CTA stages its 128 rows of A and its 128-row half of
+// B, so every SM loads 32 KB instead of 48 KB per 64-wide k-block (less L2->SM traffic, less smem read per MMA) and six
+// pipeline stages fit.  The leader CTA's single MMA thread issues tcgen05.mma.cta_group::2 for both SMs;
+// tcgen05.commit multicasts stage-release / accumulator-ready arrivals to both CTAs; the peer CTA's TMA loads complete
+// on the leader's mbarrier; the peer's epilogue warps signal "accumulator drained" on the leader's barrier remotely.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace b200 {
+
+constexpr int G2_BM = 256;        // per cluster
+constexpr int G2_BN = 256;
+constexpr int G2_BK = 64;
+constexpr int G2_STAGES = 6;
+constexpr int G2_A_BYTES = 128 * G2_BK * 2;   // per CTA: 128 rows of A
+constexpr int G2_B_BYTES = 128 * G2_BK * 2;   // per CTA: 128 of the 256 B rows
+constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;  // 32 KB
+constexpr int G2_THREADS = 192;
+constexpr int G2_SMEM = G2_STAGES * G2_STAGE_BYTES + 256 + 1024;
+
+struct Gemm2Params {
+  __nv_bfloat16* C;
+  int M, N, K, ldc;
+  int accumulate;
+  int group_m;
+  uint32_t a_lbo, a_sbo, b_lbo, b_sbo;
+};
+
+template <int A_MN, int B_MN>
+__global__ void __launch_bounds__(G2_THREADS, 1)
+gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Gemm2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + G2_STAGES;
+  uint64_t* tfull_bar = empty_bar + G2_STAGES;  // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;         // [2] (used in the leader CTA only)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  const int num_m = (p.M + G2_BM - 1) / G2_BM;
+  const int num_n = (p.N + G2_BN - 1) / G2_BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (p.K + G2_BK - 1) / G2_BK;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < G2_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 256);  // 128 epilogue threads of each CTA
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm<512>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto tile_coords = [&](int tile, int& tm, int& tn) {
+    const int group_size = p.group_m * num_n;
+    const int group = tile / group_size;
+    const int first_m = group * p.group_m;
+    const int gsz = min(p.group_m, num_m - first_m);
+    const int in_group = tile - group * group_size;
+    tm = first_m + in_group % gsz;
+    tn = in_group / gsz;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        int tm, tn;
+        tile_coords(tile, tm, tn);
+        const int m0 = tm * G2_BM + rank * 128;
+        const int n0 = tn * G2_BN + rank * 128;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * G2_STAGE_BYTES;
+          uint8_t* sB = sA + G2_A_BYTES;
+          const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);  // both CTAs' bytes land on this barrier
+          if (A_MN == 0) {
+            tma_load_2d_2sm(sA, &tmA, leader_full, kb * G2_BK, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) tma_load_2d_2sm(sA + j * (64 * G2_BK * 2), &tmA, leader_full, m0 + j * 64, kb * G2_BK);
+          }
+          if (B_MN == 0) {
+            tma_load_2d_2sm(sB, &tmB, leader_full, kb * G2_BK, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) tma_load_2d_2sm(sB + j * (64 * G2_BK * 2), &tmB, leader_full, n0 + j * 64, kb * G2_BK);
+          }
+          if (++stage == G2_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(G2_BM, G2_BN, A_MN, B_MN);
+      constexpr uint32_t a_kstep = A_MN ? 16 * 128 : 32;
+      constexpr uint32_t b_kstep = B_MN ? 16 * 128 : 32;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * G2_BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + stage * G2_STAGE_BYTES);
+          const uint32_t sB = sA + G2_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < G2_BK / 16; ++k) {
+            const uint64_t da = make_smem_desc(sA + k * a_kstep, p.a_lbo, p.a_sbo, SWZ_128B);
+            const uint64_t db = make_smem_desc(sB + k * b_kstep, p.b_lbo, p.b_sbo, SWZ_128B);
+            umma_ss_2sm(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[stage], 0x3);
+          if (++stage == G2_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2sm(&tfull_bar[buf], 0x3);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    int it = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      int tm, tn;
+      tile_coords(tile, tm, tn);
+      const int buf = it & 1;
+      mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const int row = tm * G2_BM + rank * 128 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * G2_BN;
+      __nv_bfloat16* crow = p.C + static_cast<size_t>(row) * p.ldc + tn * G2_BN;
+      const int ncols = min(G2_BN, p.N - tn * G2_BN);
+#pragma unroll 1
+      for (int c = 0; c < G2_BN / 32; ++c) {
+        if (c * 32 >= ncols) break;
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + c * 32, r);
+        tmem_ld_wait();
+        if (row < p.M) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const int col = c * 32 + v * 8;
+            if (col + 8 <= ncols) {
+              uint4* dst = reinterpret_cast<uint4*>(crow + col);
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[v * 8 + e]);
+              if (p.accumulate) {
+                uint4 old = *dst;
+                const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&old);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float2 of = __bfloat1622float2(o2[e]);
+                  f[2 * e] += of.x;
+                  f[2 * e + 1] += of.y;
+                }
+              }
+              uint4 o;
+              o.x = pack_bf16(f[0], f[1]);
+              o.y = pack_bf16(f[2], f[3]);
+              o.z = pack_bf16(f[4], f[5]);
+              o.w = pack_bf16(f[6], f[7]);
+              *dst = o;
+            } else {
+              for (int e = 0; e < 8; ++e) {
+                if (col + e < ncols) {
+                  float f = __uint_as_float(r[v * 8 + e]);
+                  if (p.accumulate) f += __bfloat162float(crow[col + e]);
+                  crow[col + e] = __float2bfloat16_rn(f);
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[buf]), 0));  // accumulator drained: tell the leader
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm<512>(tmem_base);
+  }
+}
+
+template <int A_MN, int B_MN>
+static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm2Params& p, cudaStream_t stream) {
+  auto kern = gemm_bf16_tcgen05_2sm<A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
+    attr_set = true;
+  }
+  const int num_tiles = ((p.M + G2_BM - 1) / G2_BM) * ((p.N + G2_BN - 1) / G2_BN);
+  int sms = num_sms();
+  if (sms <= 0) {
+    set_last_error("no CUDA device");
+    return B200_ERR_NODEV;
+  }
+  int clusters = sms / 2;
+  if (num_tiles < clusters) clusters = num_tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * 2);
+  cfg.blockDim = dim3(G2_THREADS);
+  cfg.dynamicSmemBytes = G2_SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  B200_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+  return B200_OK;
+}
+
+}  // namespace b200
+
+// Same contract as b200_gemm_bf16 (gemm.cu); requires M > 128 to be worthwhile.  Called by the dispatcher there.
+extern "C" int b200_gemm_bf16_2sm(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
+                                  int a_mn, int b_mn, int accumulate, cudaStream_t stream) {
+  using namespace b200;
+  B200_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % 8 == 0, "gemm: C must be 16B aligned, ldc %% 8 == 0");
+  B200_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 elements");
+  CUtensorMap tmA, tmB;
+  int rc;
+  // per-CTA boxes: 128 rows of A / B (K-major) or 64-column x 64-k boxes (MN-major)
+  if (!a_mn)
+    rc = make_tmap_2d_bf16(&tmA, A, M, K, lda, G2_BK, 128);
+  else
+    rc = make_tmap_2d_bf16(&tmA, A, K, M, lda, 64, G2_BK);
+  if (rc) return rc;
+  if (!b_mn)
+    rc = make_tmap_2d_bf16(&tmB, B, N, K, ldb, G2_BK, 128);
+  else
+    rc = make_tmap_2d_bf16(&tmB, B, K, N, ldb, 64, G2_BK);
+  if (rc) return rc;
+  Gemm2Params p;
+  p.C = reinterpret_cast<__nv_bfloat16*>(C);
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.ldc = ldc;
+  p.accumulate = accumulate;
+  p.group_m = 8;
+  const uint32_t k_lbo = 16, k_sbo = 1024, mn_lbo = 64 * G2_BK * 2, mn_sbo = 1024;
+  p.a_lbo = a_mn ? mn_lbo : k_lbo;
+  p.a_sbo = a_mn ? mn_sbo : k_sbo;
+  p.b_lbo = b_mn ? mn_lbo : k_lbo;
+  p.b_sbo = b_mn ? mn_sbo : k_sbo;
+  if (!a_mn && !b_mn) return launch_gemm2<0, 0>(tmA, tmB, p, stream);
+  if (!a_mn && b_mn) return launch_gemm2<0, 1>(tmA, tmB, p, stream);
+  if (a_mn && b_mn) return launch_gemm2<1, 1>(tmA, tmB, p, stream);
+  return launch_gemm2<1, 0>(tmA, tmB, p, stream);
+}

@@ -260,6 +260,20 @@ def attn_bwd(q, k, v, out, dout, lse, dq, dk, dv, *, scale: float, causal: bool,
     return dq, dk, dv
 
 
+# ------------------------------------------------------------------------------------------------------- KV cache
+def kv_append(k_new: torch.Tensor, v_new: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, offset: int) -> None:
+    """Write k_new / v_new [B,H,q,D] (strided) into rows [offset, offset+q) of the [B,H,capacity,D] caches, in place."""
+    lib = _lib_ready()
+    _chk_bf16(k_new, v_new, k_cache, v_cache)
+    B, H, q, D = k_new.shape
+    if k_new.stride(3) != 1 or v_new.stride(3) != 1 or k_cache.stride(3) != 1 or k_cache.stride() != v_cache.stride():
+        raise B200Error("kv_append: unit inner stride and identical k/v cache layouts required")
+    check(lib.b200_kv_append(k_new.data_ptr(), v_new.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), B, H, q, D,
+                             k_new.stride(0), k_new.stride(1), k_new.stride(2), v_new.stride(0), v_new.stride(1), v_new.stride(2),
+                             k_cache.stride(0), k_cache.stride(1), k_cache.stride(2), int(offset), k_cache.shape[2], _stream()),
+          "b200_kv_append")
+
+
 # ----------------------------------------------------------------------------------------------------------- loss
 def ce_fwd(logits: torch.Tensor, labels: torch.Tensor, shift: bool = True, ignore_index: int = -100,
            num_items: float | None = None):
