@@ -77,6 +77,9 @@ int b200_attn_bwd(const void* q, const void* k, const void* v, const void* out, 
                   int lse_stride, const int64_t* strides, float scale, float softcap, int causal, int window,
                   const int* kv_start, const int* kv_end, b200_stream_t stream);
 
+/* bring-up aid: int64[16] device buffer filled with per-role cycle counters by CTA 0 of the dK/dV kernel; NULL = off */
+int b200_debug_set_buffer(void* device_i64_buffer);
+
 /* In-place KV-cache append replacing torch.cat in DynamicLayer.update (cache_utils.py:127-146; Cache.update :1349-1381):
  * writes rows [offset, offset+q_len) of the preallocated [B,H,capacity,D] caches. */
 int b200_kv_append(const void* k_new, const void* v_new, void* k_cache, void* v_cache, int B, int H, int q_len, int D,

@@ -31,6 +31,7 @@ SIGNATURES = {
     "b200_glu_fwd": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
     "b200_glu_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "b200_add_bf16": [_p, _p, _p, _l, _p],
+    "b200_debug_set_buffer": [_p],
     "b200_kv_append": [_p, _p, _p, _p, _i, _i, _i, _i] + [_l] * 9 + [_i, _i, _p],
     "b200_ce_fwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _l, _f, _p],
     "b200_attn_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i] + [_l] * 12 + [_f, _f, _i, _i, _p, _p, _p],
