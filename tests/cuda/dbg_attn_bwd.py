@@ -19,5 +19,4 @@ lib.b200_debug_set_buffer(None)
 d = dbg.tolist(); n = max(d[2], 1)
 print(f"iters {d[2]}")
 print(f"TMA : total {d[0]} ({d[0]/n:.0f}/it)  wait q_empty {d[1]} ({d[1]/n:.0f}/it)")
-print(f"MMA : total {d[4]} ({d[4]/n:.0f}/it)  wait q_full {d[5]/n:.0f}/it  wait pds_full {d[6]/n:.0f}/it  issue {d[7]/n:.0f}/it")
-print(f"COMP(warp2, parity 0, {n//2} tiles): total {d[8]} ({d[8]/(n/2):.0f}/tile)  wait sdp_full {d[9]/(n/2):.0f}/tile  compute {d[10]/(n/2):.0f}/tile")
+print(f"MMA : total {d[4]} ({d[4]/n:.0f}/it)  wait q_full {d[5]/n:.0f}/it  wait pds_full {d[6]/n:.0f}/it  issue sdp(16xSS N64) {d[7]/n:.0f}/it  issue dvdk(8xTS N128) {d[11]/n:.0f}/it")

@@ -14,8 +14,9 @@
 
 namespace b200 {
 
-constexpr int BWD_THREADS = 576;  // TMA warp + MMA warp + 16 compute warps: per TMEM lane quarter 2 column halves x 2 tile parities,
-                                  // so two consecutive tiles are in flight in the softmax/dS stage (latency-bound otherwise)
+constexpr int BWD_THREADS = 576;  // 16 compute warps (per TMEM lane quarter: four 16-column quarters of each tile) + TMA warp + MMA warp.
+constexpr int BWD_TMA_WARP = 16;  // The single-thread MMA issuer sits in the HIGHEST warp id: the SM sub-partition arbiter favours
+constexpr int BWD_MMA_WARP = 17;  // high warp ids, and a starved issuer idles the tensor pipe (measured: 2075 vs 1280 cycles / tile).
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct AttnBwdParams {
@@ -145,19 +146,19 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sdp_full[i], 1);
-      mbar_init(&pds_full[i], 256);
+      mbar_init(&pds_full[i], 512);
     }
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == BWD_MMA_WARP) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    if (lane == 0 && n_iter > 0) {
+  if (warp == BWD_TMA_WARP) {
+    if (n_iter > 0 && elect_one()) {
       mbar_expect_tx(kv_full, 2 * KV_BYTES);
 #pragma unroll
       for (int c = 0; c < DCH; ++c) {
@@ -188,12 +189,15 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         p.dbg[2] = n_iter;
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0 && n_iter > 0) {
+  } else if (warp == BWD_MMA_WARP) {
+    if (n_iter > 0 && elect_one()) {
       constexpr uint32_t idesc_s = make_idesc_bf16(KV_TILE, Q_TILE, 0, 0);
       constexpr uint32_t idesc_acc = make_idesc_bf16(KV_TILE, D, 0, 1);
-      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), adO = smem_u32(sdO);
-      long long w_qfull = 0, w_pds = 0, t_issue = 0, t_total = DBG_ON ? clock64() : 0;
+      // descriptors are built once; per MMA only the start-address field advances (keeps the issuing thread short)
+      const uint64_t dK_k = make_smem_desc(smem_u32(sK), 16, 1024, SWZ_128B), dV_k = make_smem_desc(smem_u32(sV), 16, 1024, SWZ_128B);
+      const uint64_t dQ_k = make_smem_desc(smem_u32(sQ), 16, 1024, SWZ_128B), ddO_k = make_smem_desc(smem_u32(sdO), 16, 1024, SWZ_128B);
+      const uint64_t dQ_mn = make_smem_desc(smem_u32(sQ), Q_CHUNK, 1024, SWZ_128B), ddO_mn = make_smem_desc(smem_u32(sdO), Q_CHUNK, 1024, SWZ_128B);
+      long long w_qfull = 0, w_pds = 0, t_issue = 0, t_issue2 = 0, t_total = DBG_ON ? clock64() : 0;
       auto issue_sdp = [&](int it) {
         const int buf = it & 1;
         const int st = it % NST;
@@ -205,15 +209,13 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int kk = 0; kk < D / 16; ++kk) {
           const uint32_t oa = (kk / 4) * KV_CHUNK + (kk % 4) * 32;
           const uint32_t ob = st * Q_BYTES + (kk / 4) * Q_CHUNK + (kk % 4) * 32;
-          umma_ss(tmem_base + ST_COL + buf * 64, make_smem_desc(aK + oa, 16, 1024, SWZ_128B),
-                  make_smem_desc(aQ + ob, 16, 1024, SWZ_128B), idesc_s, kk != 0);
+          umma_ss(tmem_base + ST_COL + buf * 64, desc_advance(dK_k, oa), desc_advance(dQ_k, ob), idesc_s, kk != 0);
         }
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
           const uint32_t oa = (kk / 4) * KV_CHUNK + (kk % 4) * 32;
           const uint32_t ob = st * Q_BYTES + (kk / 4) * Q_CHUNK + (kk % 4) * 32;
-          umma_ss(tmem_base + DP_COL + buf * 64, make_smem_desc(aV + oa, 16, 1024, SWZ_128B),
-                  make_smem_desc(adO + ob, 16, 1024, SWZ_128B), idesc_s, kk != 0);
+          umma_ss(tmem_base + DP_COL + buf * 64, desc_advance(dV_k, oa), desc_advance(ddO_k, ob), idesc_s, kk != 0);
         }
         umma_commit(&sdp_full[buf]);
         DBG_ACC(t_issue);
@@ -231,16 +233,16 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
         for (int kk = 0; kk < Q_TILE / 16; ++kk) {
           // dO / Q as MN-major B: 64-col chunks Q_CHUNK apart (LBO), 8-row groups 1024 B apart (SBO), 16 rows per k-step
-          umma_ts(tmem_base + DV_COL, tmem_base + ST_COL + buf * 64 + (kk >> 1) * 32 + (kk & 1) * 8,
-                  make_smem_desc(adO + st * Q_BYTES + kk * 2048, Q_CHUNK, 1024, SWZ_128B), idesc_acc, (it | kk) != 0);
+          umma_ts(tmem_base + DV_COL, tmem_base + ST_COL + buf * 64 + kk * 16,
+                  desc_advance(ddO_mn, st * Q_BYTES + kk * 2048), idesc_acc, (it | kk) != 0);
         }
 #pragma unroll
         for (int kk = 0; kk < Q_TILE / 16; ++kk) {
-          umma_ts(tmem_base + DK_COL, tmem_base + DP_COL + buf * 64 + (kk >> 1) * 32 + (kk & 1) * 8,
-                  make_smem_desc(aQ + st * Q_BYTES + kk * 2048, Q_CHUNK, 1024, SWZ_128B), idesc_acc, (it | kk) != 0);
+          umma_ts(tmem_base + DK_COL, tmem_base + DP_COL + buf * 64 + kk * 16,
+                  desc_advance(dQ_mn, st * Q_BYTES + kk * 2048), idesc_acc, (it | kk) != 0);
         }
         umma_commit(&q_empty[st]);
-        DBG_ACC(t_issue);
+        DBG_ACC(t_issue2);
       }
       umma_commit(acc_full);
       if (DBG_ON) {
@@ -248,92 +250,84 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         p.dbg[5] = w_qfull;
         p.dbg[6] = w_pds;
         p.dbg[7] = t_issue;
+        p.dbg[11] = t_issue2;
       }
     }
   } else {
-    const int cw = warp - 2;
-    const int qd = warp & 3;          // TMEM lane quarter: hardware lets warp w touch lanes 32*(w%4).. only
-    const int half = (cw >> 2) & 1;   // which 32-column half of each 64-column tile this warp owns
-    const int par = cw >> 3;          // which tile parity (== TMEM buffer) this warp serves
+    const int qd = warp & 3;    // TMEM lane quarter: hardware lets warp w touch lanes 32*(w%4).. only
+    const int cq = warp >> 2;   // which 16-column quarter of each 64-column tile this warp owns (all 16 warps work on every
+                                // tile: the per-tile latency of this stage bounds the pipeline with only two TMEM buffers)
     const int row = qd * 32 + lane;
     const int kvpos = kv0 + row;
     const uint32_t tlane = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
     const float c2 = SOFTCAP ? p.softcap * kLog2e : p.scale * kLog2e;
     const float pre = SOFTCAP ? p.scale / p.softcap : 1.0f;
     const bool row_valid = kvpos >= kv_lo && kvpos < kv_hi;
-    long long w_sdp = 0, t_comp = 0, t_total = DBG_ON ? clock64() : 0;
+    // q rows this kv row is visible to: causal kvpos <= q + off; window kvpos > q + off - window; q < Sq
+    const int q_min = row_valid ? (mk.causal ? kvpos - off : 0) : 0x7fffffff;
+    const int q_max = min(mk.Sq, mk.window > 0 ? kvpos - off + mk.window : 0x7fffffff);
+    const int c0 = cq * 16;
 
-    for (int it = par; it < n_iter; it += 2) {
-      const int buf = par;
+    for (int it = 0; it < n_iter; ++it) {
+      const int buf = it & 1;
       const int q0 = (qt_lo + it % n_qt) * Q_TILE;
       const int st = it % NST;
-      DBG_T0();
       mbar_wait(&q_full[st], (it / NST) & 1);    // lse2 / delta rows landed (same barrier as Q / dO)
       mbar_wait(&sdp_full[buf], (it >> 1) & 1);
-      DBG_ACC(w_sdp);
       tc_fence_after();
+      uint32_t rs[16], rd[16];
+      tmem_ld_32x32b_x16(tlane + ST_COL + buf * 64 + c0, rs);
+      tmem_ld_32x32b_x16(tlane + DP_COL + buf * 64 + c0, rd);
       // block-uniform: does this (kv tile, q tile) pair need element masks?
       const bool need_mask = (kv0 < kv_lo) || (kv0 + KV_TILE > kv_hi) || (q0 + Q_TILE > mk.Sq) ||
                              (mk.causal && kv0 + KV_TILE - 1 > q0 + off) ||
                              (mk.window > 0 && kv0 <= q0 + Q_TILE - 1 + off - mk.window);
-      const float4* lrow4 = reinterpret_cast<const float4*>(sLse + st * Q_TILE + half * 32);
-      const float4* drow4 = reinterpret_cast<const float4*>(sDelta + st * Q_TILE + half * 32);
+      const float4* lrow4 = reinterpret_cast<const float4*>(sLse + st * Q_TILE + c0);
+      const float4* drow4 = reinterpret_cast<const float4*>(sDelta + st * Q_TILE + c0);
+      float lv[16], dl[16];
 #pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {   // 16 columns at a time
-        uint32_t rs[16], rd[16];
-        const int c0 = half * 32 + ch * 16;
-        tmem_ld_32x32b_x16(tlane + ST_COL + buf * 64 + c0, rs);
-        tmem_ld_32x32b_x16(tlane + DP_COL + buf * 64 + c0, rd);
-        float lv[16], dl[16];
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          const float4 a = lrow4[ch * 4 + v], d4 = drow4[ch * 4 + v];
-          lv[v * 4 + 0] = a.x; lv[v * 4 + 1] = a.y; lv[v * 4 + 2] = a.z; lv[v * 4 + 3] = a.w;
-          dl[v * 4 + 0] = d4.x; dl[v * 4 + 1] = d4.y; dl[v * 4 + 2] = d4.z; dl[v * 4 + 3] = d4.w;
-        }
-        tmem_ld_wait();
-        uint32_t pp[8], pd[8];
-#pragma unroll
-        for (int e2 = 0; e2 < 8; ++e2) {
-          float pv[2], dv[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int e = e2 * 2 + u;
-            float x = __uint_as_float(rs[e]);
-            float t = 0.f;
-            if (SOFTCAP) {
-              t = fast_tanh(x * pre);
-              x = t;
-            }
-            float pe = fast_exp2(fmaf(x, c2, -lv[e]));
-            float de = pe * (__uint_as_float(rd[e]) - dl[e]);
-            if (SOFTCAP) de *= (1.0f - t * t);
-            if (need_mask) {
-              const int qi = q0 + c0 + e;
-              const int qpos = qi + off;
-              bool ok = row_valid && qi < mk.Sq;
-              if (mk.causal) ok = ok && kvpos <= qpos;
-              if (mk.window > 0) ok = ok && kvpos > qpos - mk.window;
-              if (!ok) pe = 0.f, de = 0.f;
-            }
-            pv[u] = pe;
-            dv[u] = de;
-          }
-          pp[e2] = pack_bf16(pv[0], pv[1]);
-          pd[e2] = pack_bf16(dv[0], dv[1]);
-        }
-        tmem_st_32x32b_x8(tlane + ST_COL + buf * 64 + half * 32 + ch * 8, pp);  // inside this warp's own S^T columns
-        tmem_st_32x32b_x8(tlane + DP_COL + buf * 64 + half * 32 + ch * 8, pd);
+      for (int v = 0; v < 4; ++v) {
+        const float4 a = lrow4[v], d4 = drow4[v];
+        lv[v * 4 + 0] = a.x; lv[v * 4 + 1] = a.y; lv[v * 4 + 2] = a.z; lv[v * 4 + 3] = a.w;
+        dl[v * 4 + 0] = d4.x; dl[v * 4 + 1] = d4.y; dl[v * 4 + 2] = d4.z; dl[v * 4 + 3] = d4.w;
       }
+      tmem_ld_wait();
+      float pv[16], dv[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        float x = __uint_as_float(rs[e]);
+        float t = 0.f;
+        if (SOFTCAP) {
+          t = fast_tanh(x * pre);
+          x = t;
+        }
+        const float pe = fast_exp2(fmaf(x, c2, -lv[e]));
+        float de = pe * (__uint_as_float(rd[e]) - dl[e]);
+        if (SOFTCAP) de *= (1.0f - t * t);
+        pv[e] = pe;
+        dv[e] = de;
+      }
+      if (need_mask) {  // block-uniform branch; inside: selects only (q window [q_min, q_max) visible to this kv row)
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int qi = q0 + c0 + e;
+          const bool ok = (qi >= q_min) & (qi < q_max);
+          pv[e] = ok ? pv[e] : 0.f;
+          dv[e] = ok ? dv[e] : 0.f;
+        }
+      }
+      uint32_t pp[8], pd[8];
+#pragma unroll
+      for (int e2 = 0; e2 < 8; ++e2) {
+        pp[e2] = pack_bf16(pv[2 * e2], pv[2 * e2 + 1]);
+        pd[e2] = pack_bf16(dv[2 * e2], dv[2 * e2 + 1]);
+      }
+      // P^T / dS^T (bf16 pairs) overwrite the first 8 of this warp's own 16 S^T / dP^T columns: k-step cq of the TS MMAs
+      tmem_st_32x32b_x8(tlane + ST_COL + buf * 64 + c0, pp);
+      tmem_st_32x32b_x8(tlane + DP_COL + buf * 64 + c0, pd);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&pds_full[buf]);
-      DBG_ACC(t_comp);
-    }
-    if (DBG_ON && threadIdx.x == 64) {
-      p.dbg[8] = clock64() - t_total;
-      p.dbg[9] = w_sdp;
-      p.dbg[10] = t_comp;
     }
 
     if (n_iter > 0) {
@@ -348,7 +342,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const float mul = which == 0 ? 1.0f : p.scale;
       __nv_bfloat16* dst = which == 0 ? dvrow : dkrow;
       {
-        const int c = half * 2 + par;   // one 32-column chunk of the D-wide accumulator per warp
+        const int c = cq;   // one 32-column chunk of the D-wide accumulator per warp
         if (c >= D / 32) continue;
         uint32_t r[32];
         if (n_iter > 0) {
@@ -375,7 +369,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == BWD_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
@@ -443,19 +437,19 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sdp_full[i], 1);
-      mbar_init(&ds_full[i], 256);
+      mbar_init(&ds_full[i], 512);
     }
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == BWD_MMA_WARP) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    if (lane == 0 && n_iter > 0) {
+  if (warp == BWD_TMA_WARP) {
+    if (n_iter > 0 && elect_one()) {
       mbar_expect_tx(q_full, 2 * Q_BYTES);
 #pragma unroll
       for (int c = 0; c < DCH; ++c) {
@@ -474,11 +468,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0 && n_iter > 0) {
+  } else if (warp == BWD_MMA_WARP) {
+    if (n_iter > 0 && elect_one()) {
       constexpr uint32_t idesc_s = make_idesc_bf16(Q_TILE, KV_TILE, 0, 0);
       constexpr uint32_t idesc_acc = make_idesc_bf16(Q_TILE, D, 0, 1);
-      const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aK = smem_u32(sK), aV = smem_u32(sV);
+      const uint64_t dQ_k = make_smem_desc(smem_u32(sQ), 16, 1024, SWZ_128B), ddO_k = make_smem_desc(smem_u32(sdO), 16, 1024, SWZ_128B);
+      const uint64_t dK_k = make_smem_desc(smem_u32(sK), 16, 1024, SWZ_128B), dV_k = make_smem_desc(smem_u32(sV), 16, 1024, SWZ_128B);
+      const uint64_t dK_mn = make_smem_desc(smem_u32(sK), KV_CHUNK, 1024, SWZ_128B);
       auto issue_sdp = [&](int it) {
         const int buf = it & 1;
         const int st = it % NST;
@@ -488,15 +484,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int kk = 0; kk < D / 16; ++kk) {
           const uint32_t oa = (kk / 4) * Q_CHUNK + (kk % 4) * 32;
           const uint32_t ob = st * KV_BYTES + (kk / 4) * KV_CHUNK + (kk % 4) * 32;
-          umma_ss(tmem_base + S_COL + buf * 64, make_smem_desc(aQ + oa, 16, 1024, SWZ_128B),
-                  make_smem_desc(aK + ob, 16, 1024, SWZ_128B), idesc_s, kk != 0);
+          umma_ss(tmem_base + S_COL + buf * 64, desc_advance(dQ_k, oa), desc_advance(dK_k, ob), idesc_s, kk != 0);
         }
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
           const uint32_t oa = (kk / 4) * Q_CHUNK + (kk % 4) * 32;
           const uint32_t ob = st * KV_BYTES + (kk / 4) * KV_CHUNK + (kk % 4) * 32;
-          umma_ss(tmem_base + DP_COL + buf * 64, make_smem_desc(adO + oa, 16, 1024, SWZ_128B),
-                  make_smem_desc(aV + ob, 16, 1024, SWZ_128B), idesc_s, kk != 0);
+          umma_ss(tmem_base + DP_COL + buf * 64, desc_advance(ddO_k, oa), desc_advance(dV_k, ob), idesc_s, kk != 0);
         }
         umma_commit(&sdp_full[buf]);
       };
@@ -510,18 +504,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int st = it % NST;
 #pragma unroll
         for (int kk = 0; kk < KV_TILE / 16; ++kk) {
-          umma_ts(tmem_base + DQ_COL, tmem_base + DP_COL + buf * 64 + (kk >> 1) * 32 + (kk & 1) * 8,
-                  make_smem_desc(aK + st * KV_BYTES + kk * 2048, KV_CHUNK, 1024, SWZ_128B), idesc_acc, (it | kk) != 0);
+          umma_ts(tmem_base + DQ_COL, tmem_base + DP_COL + buf * 64 + kk * 16,
+                  desc_advance(dK_mn, st * KV_BYTES + kk * 2048), idesc_acc, (it | kk) != 0);
         }
         umma_commit(&kv_empty[st]);
       }
       umma_commit(acc_full);
     }
   } else {
-    const int cw = warp - 2;
     const int qd = warp & 3;
-    const int half = (cw >> 2) & 1;
-    const int par = cw >> 3;
+    const int cq = warp >> 2;   // 16-column quarter of each 64-column tile
     const int row = qd * 32 + lane;
     const int qrow = q0 + row;
     const int qpos = qrow + off;
@@ -537,47 +529,45 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     int r_hi = min(mk.kv_end ? mk.kv_end[b] : mk.Skv, mk.Skv), r_lo = max(mk.kv_start ? mk.kv_start[b] : 0, 0);
     if (mk.causal) r_hi = min(r_hi, qpos + 1);
     if (mk.window > 0) r_lo = max(r_lo, qpos - mk.window + 1);
+    const int c0 = cq * 16;
 
-    for (int it = par; it < n_iter; it += 2) {
-      const int buf = par;
+    for (int it = 0; it < n_iter; ++it) {
+      const int buf = it & 1;
       const int kv0 = (t_lo + it) * KV_TILE;
       mbar_wait(&sdp_full[buf], (it >> 1) & 1);
       tc_fence_after();
+      uint32_t rs[16], rd[16];
+      tmem_ld_32x32b_x16(tlane + S_COL + buf * 64 + c0, rs);
+      tmem_ld_32x32b_x16(tlane + DP_COL + buf * 64 + c0, rd);
       const bool need_mask = (kv0 + KV_TILE > hi) || (kv0 < lo) || (mk.causal && kv0 + KV_TILE - 1 > q0 + off) ||
                              (mk.window > 0 && kv0 <= q0 + Q_TILE - 1 + off - mk.window);
+      tmem_ld_wait();
+      float dv[16];
 #pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        uint32_t rs[16], rd[16];
-        const int c0 = half * 32 + ch * 16;
-        tmem_ld_32x32b_x16(tlane + S_COL + buf * 64 + c0, rs);
-        tmem_ld_32x32b_x16(tlane + DP_COL + buf * 64 + c0, rd);
-        tmem_ld_wait();
-        uint32_t pd[8];
-#pragma unroll
-        for (int e2 = 0; e2 < 8; ++e2) {
-          float dv[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int e = e2 * 2 + u;
-            float x = __uint_as_float(rs[e]);
-            float t = 0.f;
-            if (SOFTCAP) {
-              t = fast_tanh(x * pre);
-              x = t;
-            }
-            const float pe = fast_exp2(fmaf(x, c2, -my_lse2));
-            float de = pe * (__uint_as_float(rd[e]) - my_delta);
-            if (SOFTCAP) de *= (1.0f - t * t);
-            if (need_mask) {
-              const int col = kv0 + c0 + e;
-              if (col >= r_hi || col < r_lo) de = 0.f;
-            }
-            dv[u] = de;
-          }
-          pd[e2] = pack_bf16(dv[0], dv[1]);
+      for (int e = 0; e < 16; ++e) {
+        float x = __uint_as_float(rs[e]);
+        float t = 0.f;
+        if (SOFTCAP) {
+          t = fast_tanh(x * pre);
+          x = t;
         }
-        tmem_st_32x32b_x8(tlane + DP_COL + buf * 64 + half * 32 + ch * 8, pd);
+        const float pe = fast_exp2(fmaf(x, c2, -my_lse2));
+        float de = pe * (__uint_as_float(rd[e]) - my_delta);
+        if (SOFTCAP) de *= (1.0f - t * t);
+        dv[e] = de;
       }
+      if (need_mask) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int col = kv0 + c0 + e;
+          const bool ok = (col >= r_lo) & (col < r_hi);
+          dv[e] = ok ? dv[e] : 0.f;
+        }
+      }
+      uint32_t pd[8];
+#pragma unroll
+      for (int e2 = 0; e2 < 8; ++e2) pd[e2] = pack_bf16(dv[2 * e2], dv[2 * e2 + 1]);
+      tmem_st_32x32b_x8(tlane + DP_COL + buf * 64 + c0, pd);   // inside this warp's own dP columns: k-step cq of dQ += dS K
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&ds_full[buf]);
@@ -588,7 +578,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_after();
     }
     __nv_bfloat16* dst = p.dq + b * p.dq_bs + static_cast<int64_t>(qrow) * p.dq_rs + h * p.dq_hs;
-    for (int c = half * 2 + par; c < D / 32; c += 4) {   // one 32-column chunk of dQ per warp
+    for (int c = cq; c < D / 32; c += 4) {   // one 32-column chunk of dQ per warp
       uint32_t r[32];
       if (n_iter > 0) {
         tmem_ld_32x32b_x32(tlane + DQ_COL + c * 32, r);
@@ -613,7 +603,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == BWD_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }

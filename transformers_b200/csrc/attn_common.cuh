@@ -7,12 +7,12 @@ namespace b200 {
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));  // not volatile: pure, free to schedule
   return y;
 }
 __device__ __forceinline__ float fast_tanh(float x) {
   float y;
-  asm volatile("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 

@@ -89,7 +89,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync: the compiler keeps UTCHMMA / UTMALDG operands in uniform registers (no per-op ELECT loop)
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -122,7 +122,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync: the compiler keeps UTCHMMA / UTMALDG operands in uniform registers (no per-op ELECT loop)
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
       // byte advance of the descriptor start address per UMMA_K = 16 step
       constexpr uint32_t a_kstep = A_MN ? 16 * 128 : 32;

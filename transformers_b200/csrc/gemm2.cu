@@ -81,7 +81,7 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync: the compiler keeps UTCHMMA / UTMALDG operands in uniform registers (no per-op ELECT loop)
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
@@ -115,7 +115,7 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0 && elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(G2_BM, G2_BN, A_MN, B_MN);
       constexpr uint32_t a_kstep = A_MN ? 16 * 128 : 32;
       constexpr uint32_t b_kstep = B_MN ? 16 * 128 : 32;

@@ -154,6 +154,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   return d;
 }
 constexpr uint32_t SWZ_128B = 2;
+// descriptor for (base address + byte_offset): only the 14-bit start-address field changes, so one 32-bit add suffices
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t byte_offset) {
+  return desc + static_cast<uint64_t>(byte_offset >> 4);
+}
 
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 accumulation.
 //  [4,6) D fmt (1 = f32)  [7,10) A fmt (1 = bf16)  [10,13) B fmt  [13] negA [14] negB
