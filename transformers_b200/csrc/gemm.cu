@@ -295,16 +295,16 @@ extern "C" int b200_gemm_bf16_ex(const void* A, const void* B, void* C, int M, i
 extern "C" int b200_gemm_bf16_2sm(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
                                   int a_mn, int b_mn, int accumulate, cudaStream_t stream);
 
-// Dispatcher.  Measured on the full Llama-3-8B step (profiles/README.md): under the 1 kW power cap the 1-CTA 128x256
-// kernel sustains 1359 TF/s vs 1339 TF/s for the CTA-pair kernel (gemm2.cu, 256x256 tiles; faster only in short bursts
-// at K = 4096), so the 1-CTA kernel is the default; B200_GEMM_2SM=1 selects the CTA-pair kernel.
+// Dispatcher.  Measured on the full Llama-3-8B step under the 1 kW power cap (profiles/README.md): the CTA-pair kernel
+// (gemm2.cu, 256x256 tiles, 32 KB/stage/SM) sustains 1453 TF/s vs 1351 TF/s for the 1-CTA 128x256 kernel, so it is the
+// default for anything taller than one tile; B200_GEMM_1SM=1 forces the 1-CTA kernel (A/B timing, tiny shapes use it anyway).
 extern "C" int b200_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
                               int a_mn, int b_mn, int accumulate, cudaStream_t stream) {
-  static const int use_2sm = [] {
-    const char* e = getenv("B200_GEMM_2SM");
+  static const int force_1sm = [] {
+    const char* e = getenv("B200_GEMM_1SM");
     return (e && e[0] == '1') ? 1 : 0;
   }();
-  if (use_2sm && M > 128 && N > 64)
+  if (!force_1sm && M > 128 && N > 64)
     return b200_gemm_bf16_2sm(A, B, C, M, N, K, lda, ldb, ldc, a_mn, b_mn, accumulate, stream);
   return b200_gemm_bf16_ex(A, B, C, M, N, K, lda, ldb, ldc, a_mn, b_mn, accumulate, 0, stream);
 }

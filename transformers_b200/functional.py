@@ -27,11 +27,13 @@ class FusedLinearFn(torch.autograd.Function):
         x2 = x.reshape(-1, K)
         if not x2.is_contiguous():
             x2 = x2.contiguous()
-        y = ops.gemm(x2, w_fused)  # A = x [T,K] K-major, B = W [N,K] K-major
+        N = w_fused.shape[0]
+        y = torch.empty(*x.shape[:-1], N, device=x.device, dtype=x.dtype)  # returned as-is (not a view): a following
+        ops.gemm(x2, w_fused, out=y.view(-1, N))                             # all-reduce may update it in place
         ctx.save_for_backward(x2, w_fused)
         ctx.splits = [w.shape[0] for w in weights]
         ctx.x_shape = x.shape
-        return y.view(*x.shape[:-1], w_fused.shape[0])
+        return y
 
     @staticmethod
     def backward(ctx, dy):

@@ -96,8 +96,17 @@ def resolve_plan(model) -> dict:
     has_prefix = hasattr(model, prefix)
     for k, v in base.items():
         plan[(prefix + "." + k) if has_prefix else k] = v
-    for k, v in (getattr(model, "_tp_plan", None) or {}).items():
-        plan[k] = v
+    # class-level plan (e.g. {"lm_head": "colwise_gather_output"}); some transformers versions shadow it on the instance
+    # with the merged base plan, so read both
+    for klass in type(model).__mro__:
+        cls_plan = klass.__dict__.get("_tp_plan")
+        if isinstance(cls_plan, dict):
+            for k, v in cls_plan.items():
+                plan.setdefault(k, v)
+    inst_plan = getattr(model, "_tp_plan", None)
+    if isinstance(inst_plan, dict):
+        for k, v in inst_plan.items():
+            plan.setdefault(k, v)
     return plan
 
 
