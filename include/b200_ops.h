@@ -86,6 +86,15 @@ int b200_kv_append(const void* k_new, const void* v_new, void* k_cache, void* v_
                    int64_t ks_b, int64_t ks_h, int64_t ks_r, int64_t vs_b, int64_t vs_h, int64_t vs_r, int64_t cs_b,
                    int64_t cs_h, int64_t cs_r, int offset, int capacity, b200_stream_t stream);
 
+/* Mixtral experts path (MixtralExperts.forward models/mixtral/modeling_mixtral.py:69-93; grouped_mm_experts_forward
+ * integrations/moe.py:377-478): sort (token, k) pairs by expert, gather rows, [expert GEMMs = b200_gemm_bf16 on row
+ * ranges], weighted un-permute.  counts must be zeroed by the caller; offsets has E+1 entries. */
+int b200_moe_route(const int64_t* top_k_index, int* counts, int* offsets, int* cursor, int* slot, int* token_of_slot,
+                   int T, int topk, int E, b200_stream_t stream);
+int b200_moe_gather(const void* x, const int* token_of_slot, void* x_sorted, int nslots, int H, b200_stream_t stream);
+int b200_moe_combine(const void* y_sorted, const int* slot, const float* weights, void* out, int T, int topk, int H,
+                     b200_stream_t stream);
+
 /* ForCausalLMLoss (loss/loss_utils.py:32-70): shifted labels, fp32 log-sum-exp, mean over valid targets. */
 int b200_ce_fwd(const void* logits, const int64_t* labels, float* lse, float* loss_rows, float* loss_out,
                 float* denom_out, int B, int S, int V, int ld, int shift, int64_t ignore_index, float num_items,

@@ -47,6 +47,8 @@ class DecoderConfig:
     query_pre_attn_scalar: float | None = None
     tie_word_embeddings: bool = False
     pad_token_id: int | None = None  # nn.Embedding(padding_idx=...) models/llama/modeling_llama.py:350-353
+    num_local_experts: int = 0  # > 0: Mixtral sparse MoE block instead of the dense MLP (models/mixtral/modeling_mixtral.py:114-130)
+    num_experts_per_tok: int = 2
 
     @property
     def gemma(self) -> bool:
@@ -212,6 +214,43 @@ def mlp(x: torch.Tensor, w_gate: torch.Tensor, w_up: torch.Tensor, w_down: torch
     return F.linear(act_fn(F.linear(x, w_gate), act) * F.linear(x, w_up), w_down)
 
 
+def moe_router(x: torch.Tensor, w_gate: torch.Tensor, top_k: int):
+    """MixtralTopKRouter.forward models/mixtral/modeling_mixtral.py:104-111: linear -> fp32 softmax -> top-k -> renormalise."""
+    router_logits = F.linear(x, w_gate)
+    router_probs = F.softmax(router_logits.float(), dim=-1)
+    top_value, top_index = torch.topk(router_probs, top_k, dim=-1)
+    top_value = top_value / top_value.sum(dim=-1, keepdim=True)
+    return top_value, top_index
+
+
+def moe_experts(x: torch.Tensor, top_k_index: torch.Tensor, top_k_weights: torch.Tensor, gate_up: torch.Tensor,
+                down: torch.Tensor, act: str = "silu") -> torch.Tensor:
+    """MixtralExperts.forward models/mixtral/modeling_mixtral.py:69-93 (per-expert loop, index_add un-permute)."""
+    E = gate_up.shape[0]
+    final = torch.zeros_like(x)
+    expert_mask = F.one_hot(top_k_index, num_classes=E).permute(2, 1, 0)
+    for e in range(E):
+        top_k_pos, token_idx = torch.where(expert_mask[e])
+        if token_idx.numel() == 0:
+            continue
+        cur = x[token_idx]
+        gate, up = F.linear(cur, gate_up[e]).chunk(2, dim=-1)
+        h = act_fn(gate, act) * up
+        h = F.linear(h, down[e])
+        h = h * top_k_weights[token_idx, top_k_pos, None]
+        final.index_add_(0, token_idx, h.to(final.dtype))
+    return final
+
+
+def moe_block(x: torch.Tensor, p: dict, prefix: str, cfg: "DecoderConfig") -> torch.Tensor:
+    """MixtralSparseMoeBlock.forward models/mixtral/modeling_mixtral.py:121-130 (no jitter in eval)."""
+    B, S, H = x.shape
+    flat = x.view(-1, H)
+    w, idx = moe_router(flat, p[prefix + "gate.weight"], cfg.num_experts_per_tok)
+    out = moe_experts(flat, idx, w.to(flat.dtype) if False else w, p[prefix + "experts.gate_up_proj"], p[prefix + "experts.down_proj"], cfg.hidden_act)
+    return out.reshape(B, S, H)
+
+
 def causal_lm_loss(logits: torch.Tensor, labels: torch.Tensor, ignore_index: int = -100, num_items_in_batch=None):
     """ForCausalLMLoss loss/loss_utils.py:48-70 + fixed_cross_entropy :32-45."""
     vocab_size = logits.shape[-1]
@@ -265,7 +304,10 @@ def decoder_layer(x: torch.Tensor, p: dict, layer_idx: int, cfg: DecoderConfig, 
         h = rms_norm(h, p[pre + "pre_feedforward_layernorm.weight"], eps, g)
     else:
         h = rms_norm(h, p[pre + "post_attention_layernorm.weight"], eps, g)
-    h = mlp(h, p[pre + "mlp.gate_proj.weight"], p[pre + "mlp.up_proj.weight"], p[pre + "mlp.down_proj.weight"], cfg.hidden_act)
+    if cfg.num_local_experts:
+        h = moe_block(h, p, pre + "mlp.", cfg)
+    else:
+        h = mlp(h, p[pre + "mlp.gate_proj.weight"], p[pre + "mlp.up_proj.weight"], p[pre + "mlp.down_proj.weight"], cfg.hidden_act)
     if g:
         h = rms_norm(h, p[pre + "post_feedforward_layernorm.weight"], eps, g)
     return residual + h
@@ -318,4 +360,6 @@ def config_from_hf(hf_cfg) -> DecoderConfig:
         attn_logit_softcapping=d.get("attn_logit_softcapping"), final_logit_softcapping=d.get("final_logit_softcapping"),
         query_pre_attn_scalar=d.get("query_pre_attn_scalar"), tie_word_embeddings=bool(d.get("tie_word_embeddings", False)),
         pad_token_id=d.get("pad_token_id"),
+        num_local_experts=(d.get("num_local_experts") or 0) if d.get("model_type") == "mixtral" else 0,
+        num_experts_per_tok=d.get("num_experts_per_tok") or 2,
     )

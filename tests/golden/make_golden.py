@@ -20,7 +20,7 @@ import torch  # noqa: E402
 import transformers  # noqa: E402
 
 assert transformers.__file__.startswith(REF), transformers.__file__
-from transformers import Gemma2Config, Gemma2ForCausalLM, LlamaConfig, LlamaForCausalLM, MistralConfig, MistralForCausalLM, set_seed  # noqa: E402
+from transformers import Gemma2Config, Gemma2ForCausalLM, LlamaConfig, LlamaForCausalLM, MistralConfig, MistralForCausalLM, MixtralConfig, MixtralForCausalLM, set_seed  # noqa: E402
 from transformers.models.llama import modeling_llama as ml  # noqa: E402
 from transformers.models.gemma2 import modeling_gemma2 as mg  # noqa: E402
 
@@ -30,7 +30,8 @@ torch.set_num_threads(4)
 
 def model_fixture(name, cls, cfg, dtype, B=2, S=24, pad=False):
     set_seed(42)
-    model = cls._from_config(cfg, attn_implementation="eager", dtype=dtype)
+    extra = {"experts_implementation": "eager"} if hasattr(cfg, "num_local_experts") else {}  # per-expert loop = the eager path
+    model = cls._from_config(cfg, attn_implementation="eager", dtype=dtype, **extra)
     model.train()
     # non-trivial norm weights so their gradients are exercised
     with torch.no_grad():
@@ -145,19 +146,30 @@ def op_fixtures():
 
 
 if __name__ == "__main__":
-    op_fixtures()
+    if not os.environ.get("GOLDEN_ONLY"):
+        op_fixtures()
+    only = os.environ.get("GOLDEN_ONLY")  # e.g. GOLDEN_ONLY=mixtral regenerates just that family
     for dtype, tag in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
-        model_fixture(f"llama_tiny_{tag}", LlamaForCausalLM, llama_cfg(), dtype)
-        model_fixture(f"llama_tiny_padded_{tag}", LlamaForCausalLM, llama_cfg(), dtype, pad=True)
-        model_fixture(f"llama3rope_tiny_{tag}", LlamaForCausalLM, llama_cfg(rope_parameters={
-            "rope_type": "llama3", "rope_theta": 500000.0, "factor": 8.0, "low_freq_factor": 1.0, "high_freq_factor": 4.0,
-            "original_max_position_embeddings": 16}), dtype)
-        model_fixture(f"mistral_tiny_{tag}", MistralForCausalLM, MistralConfig(
-            vocab_size=160, hidden_size=64, intermediate_size=176, num_hidden_layers=2, num_attention_heads=4,
-            num_key_value_heads=2, head_dim=16, sliding_window=8, rms_norm_eps=1e-5,
-            rope_parameters={"rope_type": "default", "rope_theta": 10000.0}), dtype)
-        model_fixture(f"gemma2_tiny_{tag}", Gemma2ForCausalLM, Gemma2Config(
-            vocab_size=160, hidden_size=64, intermediate_size=176, num_hidden_layers=2, num_attention_heads=4,
-            num_key_value_heads=2, head_dim=32, sliding_window=8, query_pre_attn_scalar=32,
-            attn_logit_softcapping=50.0, final_logit_softcapping=30.0, layer_types=["sliding_attention", "full_attention"],
-            rope_parameters={"rope_type": "default", "rope_theta": 10000.0}), dtype)
+        jobs = {
+            "llama_tiny": lambda: model_fixture(f"llama_tiny_{tag}", LlamaForCausalLM, llama_cfg(), dtype),
+            "llama_tiny_padded": lambda: model_fixture(f"llama_tiny_padded_{tag}", LlamaForCausalLM, llama_cfg(), dtype, pad=True),
+            "llama3rope_tiny": lambda: model_fixture(f"llama3rope_tiny_{tag}", LlamaForCausalLM, llama_cfg(rope_parameters={
+                "rope_type": "llama3", "rope_theta": 500000.0, "factor": 8.0, "low_freq_factor": 1.0, "high_freq_factor": 4.0,
+                "original_max_position_embeddings": 16}), dtype),
+            "mistral_tiny": lambda: model_fixture(f"mistral_tiny_{tag}", MistralForCausalLM, MistralConfig(
+                vocab_size=160, hidden_size=64, intermediate_size=176, num_hidden_layers=2, num_attention_heads=4,
+                num_key_value_heads=2, head_dim=16, sliding_window=8, rms_norm_eps=1e-5,
+                rope_parameters={"rope_type": "default", "rope_theta": 10000.0}), dtype),
+            "mixtral_tiny": lambda: model_fixture(f"mixtral_tiny_{tag}", MixtralForCausalLM, MixtralConfig(
+                vocab_size=160, hidden_size=64, intermediate_size=96, num_hidden_layers=2, num_attention_heads=4,
+                num_key_value_heads=2, head_dim=16, num_local_experts=4, num_experts_per_tok=2, sliding_window=None,
+                rms_norm_eps=1e-5, rope_parameters={"rope_type": "default", "rope_theta": 10000.0}), dtype),
+            "gemma2_tiny": lambda: model_fixture(f"gemma2_tiny_{tag}", Gemma2ForCausalLM, Gemma2Config(
+                vocab_size=160, hidden_size=64, intermediate_size=176, num_hidden_layers=2, num_attention_heads=4,
+                num_key_value_heads=2, head_dim=32, sliding_window=8, query_pre_attn_scalar=32,
+                attn_logit_softcapping=50.0, final_logit_softcapping=30.0, layer_types=["sliding_attention", "full_attention"],
+                rope_parameters={"rope_type": "default", "rope_theta": 10000.0}), dtype),
+        }
+        for name, job in jobs.items():
+            if only is None or only in name:
+                job()

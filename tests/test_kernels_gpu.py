@@ -266,3 +266,39 @@ def test_kv_append_bit_exact_vs_reference_cat():
     assert layer.get_seq_length() == ref_k.shape[-2] - 10 and torch.equal(layer.keys, ref_k[:, :, :-10])
     layer.reset()
     assert layer.get_seq_length() == 0
+
+
+def test_attention_head_dim_256_forward_vs_oracle():
+    """Gemma-2-9B geometry (head_dim 256, softcap, sliding window): forward only (configs[4] is generate())."""
+    ops = _ops()
+    B, Sq, Skv, Hq, Hkv, D = 1, 300, 300, 4, 2, 256
+    q, k, v = _randn(B, Hq, Sq, D, seed=50), _randn(B, Hkv, Skv, D, seed=51), _randn(B, Hkv, Skv, D, seed=52)
+    for window, softcap in ((0, 0.0), (128, 50.0)):
+        mask = O.eager_mask(B, Sq, Skv, torch.float32, sliding_window=window or None)
+        ref, _ = O.eager_attention(q.float(), k.float(), v.float(), mask, 256**-0.5, softcap or None)
+        out, lse = ops.attn_fwd(*(t.cuda().transpose(1, 2) for t in (q, k, v)), scale=256**-0.5, causal=True, window=window,
+                                softcap=softcap)
+        torch.testing.assert_close(out.cpu().float(), ref, atol=3e-2, rtol=3e-2)
+    # decode step over a long cache
+    q1 = _randn(B, Hq, 1, D, seed=53)
+    ref, _ = O.eager_attention(q1.float(), k.float(), v.float(), None, 256**-0.5, None)
+    out, _ = ops.attn_fwd(q1.cuda().transpose(1, 2), k.cuda().transpose(1, 2), v.cuda().transpose(1, 2), scale=256**-0.5, causal=False)
+    torch.testing.assert_close(out.cpu().float(), ref, atol=3e-2, rtol=3e-2)
+
+
+def test_moe_experts_vs_oracle():
+    """Mixtral experts path (route -> gather -> per-expert GEMMs -> GLU -> GEMMs -> weighted combine) vs the oracle's
+    restatement of MixtralExperts.forward; also an expert that receives no token and top-1 routing."""
+    ops = _ops()
+    T, H, I, E = 200, 128, 256, 8
+    x = _randn(T, H, seed=60)
+    gate_up, down = _randn(E, 2 * I, H, seed=61, scale=0.05), _randn(E, H, I, seed=62, scale=0.05)
+    w_gate = _randn(E, H, seed=63, scale=0.2)
+    for topk in (2, 1):
+        tw, ti = O.moe_router(x, w_gate, topk)
+        ti = torch.where(ti == 5, torch.full_like(ti, 4), ti)  # expert 5 gets nothing
+        ref = O.moe_experts(x.float(), ti, tw, gate_up.float(), down.float())
+        ref_bf = O.moe_experts(x, ti, tw, gate_up, down)
+        out = ops.moe_experts_forward(x.cuda(), ti.cuda(), tw.cuda(), gate_up.cuda(), down.cuda())
+        torch.testing.assert_close(out.cpu().float(), ref_bf.float(), atol=2e-2, rtol=3e-2)
+        assert _rel(out, ref) < 2e-2

@@ -134,6 +134,66 @@ def test_generate_with_inplace_kv_cache_matches_default_cache():
     assert cache.get_seq_length() == 150 + 12 - 1
 
 
+def test_mixtral_forward_with_b200_experts_matches_oracle():
+    """configs[3] geometry in miniature: Mixtral forward with experts_implementation="b200" (ExpertsInterface entry) and
+    attn_implementation="b200", against the oracle's eager restatement."""
+    tf = import_transformers()
+    import transformers_b200
+
+    transformers_b200.enable()
+    cfg = tf.MixtralConfig(vocab_size=512, hidden_size=256, intermediate_size=384, num_hidden_layers=2, num_attention_heads=4,
+                           num_key_value_heads=2, head_dim=64, num_local_experts=4, num_experts_per_tok=2, sliding_window=None,
+                           rms_norm_eps=1e-5, rope_parameters={"rope_type": "default", "rope_theta": 10000.0})
+    tf.set_seed(3)
+    model = tf.MixtralForCausalLM._from_config(cfg, attn_implementation="b200", experts_implementation="eager", dtype=BF)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    ids = torch.randint(1, cfg.vocab_size, (2, 130))
+    with torch.no_grad():
+        ref32, _, _ = O.model_forward(ids, {k: v.float() for k, v in sd.items()}, O.config_from_hf(cfg))
+        refbf, _, _ = O.model_forward(ids, sd, O.config_from_hf(cfg))
+        model = model.cuda().eval()
+        transformers_b200.accelerate(model)
+        assert model.config._experts_implementation == "b200"
+        got = model(ids.cuda()).logits.float().cpu()
+    # routing is discontinuous: a token whose top-2 choice flips under bf16 noise changes its row; compare robustly
+    err = (got - ref32).abs().amax(-1)
+    base = (refbf.float() - ref32).abs().amax(-1)
+    assert (err <= 3 * base + 3e-2).float().mean() > 0.97
+    assert torch.median(err) < 3e-2
+
+
+def test_gemma2_head_dim_256_generate():
+    """configs[4] geometry in miniature: Gemma2 with head_dim 256, softcap, alternating sliding layers; generate() =
+    prefill + decode through the KV cache (in-place append layer for the full-attention layers)."""
+    tf = import_transformers()
+    import transformers_b200
+    from transformers_b200.cache import make_cache
+
+    transformers_b200.enable()
+    cfg = tf.Gemma2Config(vocab_size=512, hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2,
+                          num_key_value_heads=1, head_dim=256, sliding_window=64, query_pre_attn_scalar=256,
+                          attn_logit_softcapping=50.0, final_logit_softcapping=30.0,
+                          layer_types=["sliding_attention", "full_attention"], max_position_embeddings=512,
+                          rope_parameters={"rope_type": "default", "rope_theta": 10000.0})
+    tf.set_seed(4)
+    model = tf.Gemma2ForCausalLM._from_config(cfg, attn_implementation="b200", dtype=BF)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    ids = torch.randint(1, cfg.vocab_size, (1, 150))
+    model = model.cuda().eval()
+    transformers_b200.accelerate(model)
+    with torch.no_grad():
+        logits = model(ids.cuda()).logits.float().cpu()
+        ref, _, _ = O.model_forward(ids, {k: v.float() for k, v in sd.items()}, O.config_from_hf(cfg))
+        torch.testing.assert_close(logits, ref, atol=6e-2, rtol=6e-2)
+        # explicit dynamic caches: Gemma2's default generation config asks for a compileable hybrid/static cache, which makes
+        # generate() torch.compile the forward (minutes, and pointless around opaque C-ABI launches)
+        from transformers.cache_utils import DynamicCache
+
+        a = model.generate(ids.cuda(), max_new_tokens=6, do_sample=False, past_key_values=DynamicCache(config=model.config))
+        b = model.generate(ids.cuda(), max_new_tokens=6, do_sample=False, past_key_values=make_cache(model.config))
+    assert a.shape == (1, 156) and torch.equal(a, b)
+
+
 def test_switch_back_to_sdpa_same_model():
     import transformers_b200
 

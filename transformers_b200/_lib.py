@@ -33,6 +33,9 @@ SIGNATURES = {
     "b200_add_bf16": [_p, _p, _p, _l, _p],
     "b200_debug_set_buffer": [_p],
     "b200_kv_append": [_p, _p, _p, _p, _i, _i, _i, _i] + [_l] * 9 + [_i, _i, _p],
+    "b200_moe_route": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "b200_moe_gather": [_p, _p, _p, _i, _i, _p],
+    "b200_moe_combine": [_p, _p, _p, _p, _i, _i, _i, _p],
     "b200_ce_fwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _l, _f, _p],
     "b200_attn_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i] + [_l] * 12 + [_f, _f, _i, _i, _p, _p, _p],
     "b200_attn_bwd": [_p] * 10 + [_i] * 7 + [_p, _f, _f, _i, _i, _p, _p, _p],

@@ -61,13 +61,13 @@ __device__ __forceinline__ KvRange kv_range(const AttnFwdParams& p, int b, int q
 }
 
 template <int D, bool SOFTCAP>
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+__global__ void __launch_bounds__(ATT_THREADS, D <= 128 ? 2 : 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, AttnFwdParams p) {
   constexpr int DCH = D / 64;                 // 64-wide (128 B) column chunks per row
   constexpr int TILE_BYTES = 128 * D * 2;     // one 128 x D bf16 tile
   constexpr int CHUNK_BYTES = 128 * 128;      // one 128-row x 64-col chunk
-  constexpr uint32_t TMEM_COLS = 256;
+  constexpr uint32_t TMEM_COLS = D <= 128 ? 256 : 512;  // S (128) + O (D) fp32 columns; head_dim 256 (Gemma-2) takes the whole TMEM
   constexpr uint32_t S_COL = 0, P_COL = 0, O_COL = 128;
 
   extern __shared__ uint8_t smem_raw[];
@@ -332,7 +332,7 @@ extern "C" int b200_attn_fwd(const void* q, const void* k, const void* v, void* 
                              int64_t o_rs, int64_t o_hs, float scale, float softcap, int causal, int window,
                              const int* kv_start, const int* kv_end, cudaStream_t stream) {
   using namespace b200;
-  B200_REQUIRE(D == 64 || D == 128, "attn_fwd: head_dim %d not supported (64 or 128)", D);
+  B200_REQUIRE(D == 64 || D == 128 || D == 256, "attn_fwd: head_dim %d not supported (64, 128 or 256)", D);
   B200_REQUIRE(Hkv > 0 && Hq % Hkv == 0, "attn_fwd: Hq=%d must be a multiple of Hkv=%d", Hq, Hkv);
   B200_REQUIRE(o_rs % 8 == 0 && o_hs % 8 == 0 && o_bs % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                "attn_fwd: output must be 16B aligned with strides multiple of 8");
@@ -361,6 +361,7 @@ extern "C" int b200_attn_fwd(const void* q, const void* k, const void* v, void* 
   p.kv_start = kv_start;
   p.kv_end = kv_end;
   const bool sc = softcap > 0.f;
+  if (D == 256) return sc ? launch_attn_fwd<256, true>(tq, tk, tv, p, stream) : launch_attn_fwd<256, false>(tq, tk, tv, p, stream);
   if (D == 128) return sc ? launch_attn_fwd<128, true>(tq, tk, tv, p, stream) : launch_attn_fwd<128, false>(tq, tk, tv, p, stream);
   return sc ? launch_attn_fwd<64, true>(tq, tk, tv, p, stream) : launch_attn_fwd<64, false>(tq, tk, tv, p, stream);
 }

@@ -73,11 +73,42 @@ def b200_attention_mask(batch_size, q_length, kv_length, q_offset=0, kv_offset=0
     return attention_mask
 
 
+# ---------------------------------------------------------------------------------------------- experts registry entry
+def b200_experts_forward(self, hidden_states, top_k_index, top_k_weights):
+    """ExpertsInterface entry (integrations/moe.py:481-506, call site :568-570): fn(module, hidden_states [T,H],
+    top_k_index [T,k] int64, top_k_weights [T,k]) -> [T,H].  The module supplies gate_up_proj [E,2I,H], down_proj [E,H,I]
+    and act_fn (MixtralExperts models/mixtral/modeling_mixtral.py:56-93).  Inference path (no autograd)."""
+    from . import ops
+
+    if torch.is_grad_enabled() and (hidden_states.requires_grad or self.gate_up_proj.requires_grad):
+        raise B200Error("b200 experts: backward through the MoE path is not implemented yet (use it under torch.no_grad())")
+    if getattr(self, "is_transposed", False) or getattr(self, "has_bias", False) or not getattr(self, "has_gate", True):
+        raise B200Error("b200 experts: only concatenated, untransposed, bias-free gate_up_proj experts are supported")
+    act = getattr(self.config, "hidden_act", "silu")
+    if act not in ("silu", "gelu_pytorch_tanh"):
+        raise B200Error(f"b200 experts: activation {act} not supported")
+    shape = hidden_states.shape
+    x = hidden_states.reshape(-1, shape[-1])
+    out = ops.moe_experts_forward(x, top_k_index, top_k_weights, self.gate_up_proj, self.down_proj, act == "gelu_pytorch_tanh")
+    return out.view(shape)
+
+
 # -------------------------------------------------------------------------------------------------------- class maps
+_CLASS_MAP = None
+
+
 def _class_map() -> dict:
+    global _CLASS_MAP
+    if _CLASS_MAP is None:
+        _CLASS_MAP = _build_class_map()
+    return _CLASS_MAP
+
+
+def _build_class_map() -> dict:
     from transformers.models.gemma2 import modeling_gemma2 as g2
     from transformers.models.llama import modeling_llama as ll
     from transformers.models.mistral import modeling_mistral as mi
+    from transformers.models.mixtral import modeling_mixtral as mx
 
     mk = M.make_class
     return {
@@ -87,6 +118,8 @@ def _class_map() -> dict:
         "MistralRMSNorm": mk(mi.MistralRMSNorm, M.B200RMSNormMixin),
         "MistralMLP": mk(mi.MistralMLP, M.B200MLPMixin),
         "MistralAttention": mk(mi.MistralAttention, M.B200AttentionMixin),
+        "MixtralRMSNorm": mk(mx.MixtralRMSNorm, M.B200RMSNormMixin),
+        "MixtralAttention": mk(mx.MixtralAttention, M.B200AttentionMixin),
         "Gemma2RMSNorm": mk(g2.Gemma2RMSNorm, M.B200RMSNormMixin, _b200_gemma=True),
         "Gemma2MLP": mk(g2.Gemma2MLP, M.B200MLPMixin),
         "Gemma2Attention": mk(g2.Gemma2Attention, M.B200AttentionMixin),
@@ -100,6 +133,12 @@ def enable(patch_modules: bool = True) -> None:
 
     AttentionInterface.register(ATTN_NAME, b200_attention_forward)
     AttentionMaskInterface.register(ATTN_NAME, b200_attention_mask)
+    try:  # Mixtral-style experts (config 4): selected with experts_implementation="b200"
+        from transformers.integrations.moe import ExpertsInterface
+
+        ExpertsInterface.register(ATTN_NAME, b200_experts_forward)
+    except ImportError:  # pragma: no cover - very old transformers
+        pass
     if patch_modules and not _enabled:
         from transformers.monkey_patching import register_patch_mapping
 
@@ -141,4 +180,13 @@ def accelerate(model: nn.Module, attn: bool = True, head_and_loss: bool = True) 
             model.loss_function = b200_causal_lm_loss
     if attn and hasattr(model, "set_attn_implementation"):
         model.set_attn_implementation(ATTN_NAME)
+    if attn and any(hasattr(m, "gate_up_proj") and hasattr(m, "num_experts") for m in model.modules()):
+        # MoE experts modules dispatch on config._experts_implementation at call time (integrations/moe.py:568-570); older
+        # transformers only validate the built-in names at construction, so the switch happens here
+        cfgs = [model.config] + ([model.config.get_text_config()] if hasattr(model.config, "get_text_config") else [])
+        for c in cfgs:
+            try:
+                c._experts_implementation = ATTN_NAME
+            except Exception:
+                c._experts_implementation_internal = ATTN_NAME
     return model

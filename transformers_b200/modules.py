@@ -193,6 +193,8 @@ _CLASS_CACHE: dict = {}
 
 def make_class(base: type, mixin: type, **attrs) -> type:
     """``class B200<Base>(mixin, base)`` -- created once per reference class, picklable by name lookup."""
+    if issubclass(base, mixin):  # already one of ours (e.g. a module attribute left patched by apply_patches)
+        return base
     key = (base, mixin, tuple(sorted(attrs.items())))
     if key not in _CLASS_CACHE:
         name = "B200" + base.__name__

@@ -17,7 +17,7 @@ from ._lib import check as _check
 BF16 = torch.bfloat16
 
 # kernels launched per C-ABI entry point
-_KERNELS_PER_CALL = {"b200_rmsnorm_bwd": 2, "b200_ce_fwd": 2, "b200_attn_bwd": 3}
+_KERNELS_PER_CALL = {"b200_rmsnorm_bwd": 2, "b200_ce_fwd": 2, "b200_attn_bwd": 3, "b200_moe_route": 3}
 
 
 def check(rc: int, what: str) -> None:
@@ -272,6 +272,47 @@ def kv_append(k_new: torch.Tensor, v_new: torch.Tensor, k_cache: torch.Tensor, v
                              k_new.stride(0), k_new.stride(1), k_new.stride(2), v_new.stride(0), v_new.stride(1), v_new.stride(2),
                              k_cache.stride(0), k_cache.stride(1), k_cache.stride(2), int(offset), k_cache.shape[2], _stream()),
           "b200_kv_append")
+
+
+# ------------------------------------------------------------------------------------------------------------ MoE
+def moe_experts_forward(x: torch.Tensor, top_k_index: torch.Tensor, top_k_weights: torch.Tensor, gate_up: torch.Tensor,
+                        down: torch.Tensor, gelu: bool = False) -> torch.Tensor:
+    """x [T,H] bf16, top_k_index [T,k] int64, top_k_weights [T,k], gate_up [E,2I,H], down [E,H,I] -> [T,H] (inference)."""
+    lib = _lib_ready()
+    _chk_bf16(x, gate_up, down)
+    T, H = x.shape
+    k = top_k_index.shape[1]
+    E, I2, _ = gate_up.shape
+    I = I2 // 2
+    dev = x.device
+    n = T * k
+    idx = top_k_index.contiguous().to(torch.int64)
+    w = top_k_weights.contiguous().to(torch.float32)
+    counts = torch.zeros(E, device=dev, dtype=torch.int32)
+    offsets = torch.empty(E + 1, device=dev, dtype=torch.int32)
+    cursor = torch.empty(E, device=dev, dtype=torch.int32)
+    slot = torch.empty(n, device=dev, dtype=torch.int32)
+    tok = torch.empty(n, device=dev, dtype=torch.int32)
+    check(lib.b200_moe_route(idx.data_ptr(), counts.data_ptr(), offsets.data_ptr(), cursor.data_ptr(), slot.data_ptr(),
+                             tok.data_ptr(), T, k, E, _stream()), "b200_moe_route")
+    xs = torch.empty(n, H, device=dev, dtype=BF16)
+    x = x.contiguous()
+    check(lib.b200_moe_gather(x.data_ptr(), tok.data_ptr(), xs.data_ptr(), n, H, _stream()), "b200_moe_gather")
+    off = offsets.tolist()  # one host sync per MoE block: the expert GEMM shapes are host-side launch parameters
+    gu = torch.empty(n, 2 * I, device=dev, dtype=BF16)
+    ys = torch.empty(n, H, device=dev, dtype=BF16)
+    for e in range(E):
+        lo, hi = off[e], off[e + 1]
+        if hi > lo:
+            gemm(xs[lo:hi], gate_up[e], out=gu[lo:hi])
+    act = glu_fwd(gu, gelu)
+    for e in range(E):
+        lo, hi = off[e], off[e + 1]
+        if hi > lo:
+            gemm(act[lo:hi], down[e], out=ys[lo:hi])
+    out = torch.empty(T, H, device=dev, dtype=BF16)
+    check(lib.b200_moe_combine(ys.data_ptr(), slot.data_ptr(), w.data_ptr(), out.data_ptr(), T, k, H, _stream()), "b200_moe_combine")
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------------- loss
