@@ -211,6 +211,8 @@ def run_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -317,12 +319,13 @@ def run_b200(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak" if parallelism == "dp" and world > 1 else "strong", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": "Llama-3-8B bf16 forward+backward seq=4096 batch=4 on 1xB200 (configs[1])" if args.layers == 32
+            "config": {"workload": (f"Llama-3-8B bf16 forward+backward seq={S} batch={B} on 1xB200 (configs[1])" if world == 1 else
+                                    f"Llama-3-8B bf16 forward+backward seq={S} batch={B}, tp_plan across {world}xB200 (configs[2])") if args.layers == 32
                        else f"DEBUG {args.layers}-layer model -- not the named config", "model": "Llama-3-8B (random init)",
                        "global_batch": B * replicas, "seq_len": S, "parallelism": f"{parallelism}{world}" if world > 1 else "single",
                        "l2": "working set (16 GB weights + activations) >> 126 MB L2; no explicit flush needed",
                        "lm_head_and_loss": "included (b200 GEMM + fused CE kernels)"},
-            "loss": float(loss), "model_tflops_per_gpu": per_gpu_tf,
+            "loss": float(loss.detach()), "model_tflops_per_gpu": per_gpu_tf,
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": ids_host.numel() * 8 * replicas,
                     "d2h_bytes_per_step": 4 * replicas, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,

@@ -273,130 +273,139 @@ template <bool BWD>
 __global__ void rope_kernel(__nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ cos_t,
                             const __nv_bfloat16* __restrict__ sin_t, int T, int S, int n_rot, int D, int row_stride,
                             int cos_batch_stride) {
-  // one thread handles 8 elements of the first half and the matching 8 of the second half
+  // blockIdx.x = token row; threads walk (head, 16-byte chunk of the first half); no per-element integer division
   const int half8 = D / 16;  // uint4 chunks per half
-  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const size_t total = static_cast<size_t>(T) * n_rot * half8;
-  if (idx >= total) return;
-  const int c = idx % half8;
-  const int h = (idx / half8) % n_rot;
-  const int t = idx / (static_cast<size_t>(half8) * n_rot);
-  const int b = t / S, s = t % S;
-  __nv_bfloat16* base = qkv + static_cast<size_t>(t) * row_stride + h * D;
-  const __nv_bfloat16* cb = cos_t + static_cast<size_t>(b) * cos_batch_stride + static_cast<size_t>(s) * D;
-  const __nv_bfloat16* sb = sin_t + static_cast<size_t>(b) * cos_batch_stride + static_cast<size_t>(s) * D;
-  uint4* p1 = reinterpret_cast<uint4*>(base) + c;
-  uint4* p2 = reinterpret_cast<uint4*>(base + D / 2) + c;
-  float x1[8], x2[8], c1[8], c2[8], s1[8], s2[8], o1[8], o2[8];
-  unpack8(*p1, x1);
-  unpack8(*p2, x2);
-  unpack8(__ldg(reinterpret_cast<const uint4*>(cb) + c), c1);
-  unpack8(__ldg(reinterpret_cast<const uint4*>(cb + D / 2) + c), c2);
-  unpack8(__ldg(reinterpret_cast<const uint4*>(sb) + c), s1);
-  unpack8(__ldg(reinterpret_cast<const uint4*>(sb + D / 2) + c), s2);
+  const int t = blockIdx.x;
+  const int b = t / S, s_pos = t - b * S;
+  __nv_bfloat16* row = qkv + static_cast<size_t>(t) * row_stride;
+  const __nv_bfloat16* cb = cos_t + static_cast<size_t>(b) * cos_batch_stride + static_cast<size_t>(s_pos) * D;
+  const __nv_bfloat16* sb = sin_t + static_cast<size_t>(b) * cos_batch_stride + static_cast<size_t>(s_pos) * D;
+  for (int i = threadIdx.x; i < n_rot * half8; i += blockDim.x) {
+    const int h = i / half8, c = i - h * half8;
+    __nv_bfloat16* base = row + h * D;
+    uint4* p1 = reinterpret_cast<uint4*>(base) + c;
+    uint4* p2 = reinterpret_cast<uint4*>(base + D / 2) + c;
+    float x1[8], x2[8], c1[8], c2[8], s1[8], s2[8], o1[8], o2[8];
+    unpack8(*p1, x1);
+    unpack8(*p2, x2);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(cb) + c), c1);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(cb + D / 2) + c), c2);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(sb) + c), s1);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(sb + D / 2) + c), s2);
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    if (!BWD) {
-      o1[e] = bf16_round(x1[e] * c1[e]) + bf16_round(-x2[e] * s1[e]);
-      o2[e] = bf16_round(x2[e] * c2[e]) + bf16_round(x1[e] * s2[e]);
-    } else {
-      o1[e] = x1[e] * c1[e] + x2[e] * s2[e];
-      o2[e] = x2[e] * c2[e] - x1[e] * s1[e];
+    for (int e = 0; e < 8; ++e) {
+      if (!BWD) {
+        o1[e] = bf16_round(x1[e] * c1[e]) + bf16_round(-x2[e] * s1[e]);
+        o2[e] = bf16_round(x2[e] * c2[e]) + bf16_round(x1[e] * s2[e]);
+      } else {
+        o1[e] = x1[e] * c1[e] + x2[e] * s2[e];
+        o2[e] = x2[e] * c2[e] - x1[e] * s1[e];
+      }
     }
+    *p1 = pack8(o1);
+    *p2 = pack8(o2);
   }
-  *p1 = pack8(o1);
-  *p2 = pack8(o2);
 }
 
 // ------------------------------------------------------------------------------------------------ gated MLP activation
 // reference: LlamaMLP.forward models/llama/modeling_llama.py:174-176: h = bf16( bf16(act(g)) * u )
 //   act = silu (activations.py:92-103) or gelu(approximate="tanh") (activations.py:30-49, Gemma)
-__device__ __forceinline__ float act_fwd(float g, int gelu) {
-  if (!gelu) return g / (1.0f + __expf(-g));
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  return 0.5f * g * (1.0f + tanhf(k0 * (g + k1 * g * g * g)));
+// One transcendental per element: sigmoid(g) = rcp(1 + 2^(-g*log2e)) (MUFU.EX2 + MUFU.RCP) or tanh.approx (MUFU.TANH); the
+// first version used IEEE division and recomputed the exponential for the gradient, which made glu_bwd ALU-bound
+// (~50 instructions per element, 0.46 ms of pure issue per call at the Llama-3-8B shape).
+__device__ __forceinline__ float fast_tanhf(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-__device__ __forceinline__ float act_grad(float g, int gelu) {
+__device__ __forceinline__ void act_fwd_grad(float g, int gelu, float& act, float& dact) {
   if (!gelu) {
-    const float s = 1.0f / (1.0f + __expf(-g));
-    return s * (1.0f + g * (1.0f - s));
+    const float s = __frcp_rn(1.0f + __expf(-g));
+    act = g * s;
+    dact = s * (1.0f + g * (1.0f - s));
+  } else {
+    const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+    const float g2 = g * g;
+    const float t = fast_tanhf(k0 * g * (1.0f + k1 * g2));
+    act = 0.5f * g * (1.0f + t);
+    dact = 0.5f * (1.0f + t) + 0.5f * g * (1.0f - t * t) * k0 * (1.0f + 3.0f * k1 * g2);
   }
+}
+__device__ __forceinline__ float act_fwd(float g, int gelu) {
+  if (!gelu) return g * __frcp_rn(1.0f + __expf(-g));
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  const float t = tanhf(k0 * (g + k1 * g * g * g));
-  return 0.5f * (1.0f + t) + 0.5f * g * (1.0f - t * t) * k0 * (1.0f + 3.0f * k1 * g * g);
+  return 0.5f * g * (1.0f + fast_tanhf(k0 * g * (1.0f + k1 * g * g)));
 }
 
-constexpr int EW_UNROLL = 4;  // independent 16-byte chunks per thread (loads issued before any use)
+// 2-D launch: blockIdx.y walks GLU_ROWS token rows, threads walk 16-byte column chunks -> no integer division per element
+// (a 64-bit div/mod per chunk made the first version ALU-bound: ncu sm__throughput 67 % at 4 TB/s).
+constexpr int GLU_ROWS = 4;
 
 __global__ void __launch_bounds__(256)
 glu_fwd_kernel(const __nv_bfloat16* __restrict__ gate, const __nv_bfloat16* __restrict__ up,
                __nv_bfloat16* __restrict__ out, int T, int I8, int ld_gu, int ld_out, int gelu) {
-  const size_t total = static_cast<size_t>(T) * I8;
-  const size_t base = static_cast<size_t>(blockIdx.x) * (blockDim.x * EW_UNROLL) + threadIdx.x;
-  uint4 gv[EW_UNROLL], uv[EW_UNROLL];
-  size_t tt[EW_UNROLL];
-  int cc[EW_UNROLL];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t0 = blockIdx.y * GLU_ROWS;
+  if (c >= I8) return;
+  uint4 gv[GLU_ROWS], uv[GLU_ROWS];
 #pragma unroll
-  for (int j = 0; j < EW_UNROLL; ++j) {
-    const size_t idx = base + static_cast<size_t>(j) * blockDim.x;
-    if (idx < total) {
-      cc[j] = idx % I8;
-      tt[j] = idx / I8;
-      gv[j] = __ldcs(reinterpret_cast<const uint4*>(gate + tt[j] * ld_gu) + cc[j]);
-      uv[j] = __ldcs(reinterpret_cast<const uint4*>(up + tt[j] * ld_gu) + cc[j]);
+  for (int j = 0; j < GLU_ROWS; ++j) {
+    const int t = t0 + j;
+    if (t < T) {
+      gv[j] = __ldg(reinterpret_cast<const uint4*>(gate + static_cast<size_t>(t) * ld_gu) + c);
+      uv[j] = __ldg(reinterpret_cast<const uint4*>(up + static_cast<size_t>(t) * ld_gu) + c);
     }
   }
 #pragma unroll
-  for (int j = 0; j < EW_UNROLL; ++j) {
-    const size_t idx = base + static_cast<size_t>(j) * blockDim.x;
-    if (idx < total) {
+  for (int j = 0; j < GLU_ROWS; ++j) {
+    const int t = t0 + j;
+    if (t < T) {
       float g[8], u[8], o[8];
       unpack8(gv[j], g);
       unpack8(uv[j], u);
 #pragma unroll
       for (int e = 0; e < 8; ++e) o[e] = bf16_round(act_fwd(g[e], gelu)) * u[e];
-      *(reinterpret_cast<uint4*>(out + tt[j] * ld_out) + cc[j]) = pack8(o);
+      *(reinterpret_cast<uint4*>(out + static_cast<size_t>(t) * ld_out) + c) = pack8(o);
     }
   }
 }
 
-constexpr int GLU_BWD_UNROLL = 2;  // 5 streams per chunk: fewer chunks per thread keeps 4 blocks/SM resident
 // dgate, dup written to dgu (same layout as gate/up).
+constexpr int GLU_BWD_ROWS = 2;
 __global__ void __launch_bounds__(256)
 glu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ gate,
                const __nv_bfloat16* __restrict__ up, __nv_bfloat16* __restrict__ dgate,
                __nv_bfloat16* __restrict__ dup, int T, int I8, int ld_dh, int ld_gu, int ld_dgu, int gelu) {
-  const size_t total = static_cast<size_t>(T) * I8;
-  const size_t base = static_cast<size_t>(blockIdx.x) * (blockDim.x * GLU_BWD_UNROLL) + threadIdx.x;
-  uint4 dv[GLU_BWD_UNROLL], gv[GLU_BWD_UNROLL], uv[GLU_BWD_UNROLL];
-  size_t tt[GLU_BWD_UNROLL];
-  int cc[GLU_BWD_UNROLL];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t0 = blockIdx.y * GLU_BWD_ROWS;
+  if (c >= I8) return;
+  uint4 dv[GLU_BWD_ROWS], gv[GLU_BWD_ROWS], uv[GLU_BWD_ROWS];
 #pragma unroll
-  for (int j = 0; j < GLU_BWD_UNROLL; ++j) {
-    const size_t idx = base + static_cast<size_t>(j) * blockDim.x;
-    if (idx < total) {
-      cc[j] = idx % I8;
-      tt[j] = idx / I8;
-      dv[j] = __ldcs(reinterpret_cast<const uint4*>(dh + tt[j] * ld_dh) + cc[j]);
-      gv[j] = __ldcs(reinterpret_cast<const uint4*>(gate + tt[j] * ld_gu) + cc[j]);
-      uv[j] = __ldcs(reinterpret_cast<const uint4*>(up + tt[j] * ld_gu) + cc[j]);
+  for (int j = 0; j < GLU_BWD_ROWS; ++j) {
+    const int t = t0 + j;
+    if (t < T) {
+      dv[j] = __ldg(reinterpret_cast<const uint4*>(dh + static_cast<size_t>(t) * ld_dh) + c);
+      gv[j] = __ldg(reinterpret_cast<const uint4*>(gate + static_cast<size_t>(t) * ld_gu) + c);
+      uv[j] = __ldg(reinterpret_cast<const uint4*>(up + static_cast<size_t>(t) * ld_gu) + c);
     }
   }
 #pragma unroll
-  for (int j = 0; j < GLU_BWD_UNROLL; ++j) {
-    const size_t idx = base + static_cast<size_t>(j) * blockDim.x;
-    if (idx < total) {
+  for (int j = 0; j < GLU_BWD_ROWS; ++j) {
+    const int t = t0 + j;
+    if (t < T) {
       float d[8], g[8], u[8], dg[8], du[8];
       unpack8(dv[j], d);
       unpack8(gv[j], g);
       unpack8(uv[j], u);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        du[e] = d[e] * bf16_round(act_fwd(g[e], gelu));
-        dg[e] = bf16_round(d[e] * u[e]) * act_grad(g[e], gelu);
+        float a, da;
+        act_fwd_grad(g[e], gelu, a, da);
+        du[e] = d[e] * bf16_round(a);
+        dg[e] = bf16_round(d[e] * u[e]) * da;
       }
-      *(reinterpret_cast<uint4*>(dgate + tt[j] * ld_dgu) + cc[j]) = pack8(dg);
-      *(reinterpret_cast<uint4*>(dup + tt[j] * ld_dgu) + cc[j]) = pack8(du);
+      *(reinterpret_cast<uint4*>(dgate + static_cast<size_t>(t) * ld_dgu) + c) = pack8(dg);
+      *(reinterpret_cast<uint4*>(dup + static_cast<size_t>(t) * ld_dgu) + c) = pack8(du);
     }
   }
 }
@@ -654,12 +663,14 @@ extern "C" int b200_rope(void* qkv, const void* cos_t, const void* sin_t, int B,
   const size_t total = static_cast<size_t>(T) * n_rot * (D / 16);
   if (total == 0) return B200_OK;
   const int cbs = cos_batch == 1 ? 0 : S * D;
+  int threads = n_rot * (D / 16);
+  threads = threads > 512 ? 512 : ((threads + 31) / 32) * 32;
   if (bwd)
-    rope_kernel<true><<<ceil_div(total, 256), 256, 0, stream>>>(
+    rope_kernel<true><<<T, threads, 0, stream>>>(
         reinterpret_cast<__nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(cos_t),
         reinterpret_cast<const __nv_bfloat16*>(sin_t), T, S, n_rot, D, row_stride, cbs);
   else
-    rope_kernel<false><<<ceil_div(total, 256), 256, 0, stream>>>(
+    rope_kernel<false><<<T, threads, 0, stream>>>(
         reinterpret_cast<__nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(cos_t),
         reinterpret_cast<const __nv_bfloat16*>(sin_t), T, S, n_rot, D, row_stride, cbs);
   B200_CHECK_CUDA(cudaGetLastError());
@@ -669,9 +680,8 @@ extern "C" int b200_rope(void* qkv, const void* cos_t, const void* sin_t, int B,
 extern "C" int b200_glu_fwd(const void* gate, const void* up, void* out, int T, int I, int ld_gu, int ld_out, int gelu,
                             cudaStream_t stream) {
   B200_REQUIRE(I % 8 == 0 && ld_gu % 8 == 0 && ld_out % 8 == 0, "glu_fwd: I=%d must be a multiple of 8", I);
-  const size_t total = static_cast<size_t>(T) * (I / 8);
-  if (total == 0) return B200_OK;
-  glu_fwd_kernel<<<ceil_div(total, 256 * EW_UNROLL), 256, 0, stream>>>(
+  if (T == 0 || I == 0) return B200_OK;
+  glu_fwd_kernel<<<dim3(ceil_div(I / 8, 256), ceil_div(T, GLU_ROWS)), 256, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(gate), reinterpret_cast<const __nv_bfloat16*>(up),
       reinterpret_cast<__nv_bfloat16*>(out), T, I / 8, ld_gu, ld_out, gelu);
   B200_CHECK_CUDA(cudaGetLastError());
@@ -681,9 +691,8 @@ extern "C" int b200_glu_fwd(const void* gate, const void* up, void* out, int T, 
 extern "C" int b200_glu_bwd(const void* dh, const void* gate, const void* up, void* dgate, void* dup, int T, int I,
                             int ld_dh, int ld_gu, int ld_dgu, int gelu, cudaStream_t stream) {
   B200_REQUIRE(I % 8 == 0 && ld_gu % 8 == 0 && ld_dh % 8 == 0 && ld_dgu % 8 == 0, "glu_bwd: I=%d must be a multiple of 8", I);
-  const size_t total = static_cast<size_t>(T) * (I / 8);
-  if (total == 0) return B200_OK;
-  glu_bwd_kernel<<<ceil_div(total, 256 * GLU_BWD_UNROLL), 256, 0, stream>>>(
+  if (T == 0 || I == 0) return B200_OK;
+  glu_bwd_kernel<<<dim3(ceil_div(I / 8, 256), ceil_div(T, GLU_BWD_ROWS)), 256, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(dh), reinterpret_cast<const __nv_bfloat16*>(gate),
       reinterpret_cast<const __nv_bfloat16*>(up), reinterpret_cast<__nv_bfloat16*>(dgate),
       reinterpret_cast<__nv_bfloat16*>(dup), T, I / 8, ld_dh, ld_gu, ld_dgu, gelu);

@@ -19,7 +19,8 @@ constexpr int G2_A_BYTES = 128 * G2_BK * 2;   // per CTA: 128 rows of A
 constexpr int G2_B_BYTES = 128 * G2_BK * 2;   // per CTA: 128 of the 256 B rows
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;  // 32 KB
 constexpr int G2_THREADS = 192;
-constexpr int G2_SMEM = G2_STAGES * G2_STAGE_BYTES + 256 + 1024;
+constexpr int G2_EPI_BYTES = 4 * 2 * 4096;  // 4 epilogue warps x 2 staging buffers x (32 rows x 128 B), 128B-swizzled for the TMA store
+constexpr int G2_SMEM = G2_STAGES * G2_STAGE_BYTES + G2_EPI_BYTES + 256 + 1024;
 
 struct Gemm2Params {
   __nv_bfloat16* C;
@@ -31,10 +32,12 @@ struct Gemm2Params {
 
 template <int A_MN, int B_MN>
 __global__ void __launch_bounds__(G2_THREADS, 1)
-gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Gemm2Params p) {
+gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmC, Gemm2Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE_BYTES);
+  uint8_t* epi_smem = smem + G2_STAGES * G2_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + G2_EPI_BYTES);
   uint64_t* empty_bar = full_bar + G2_STAGES;
   uint64_t* tfull_bar = empty_bar + G2_STAGES;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;         // [2] (used in the leader CTA only)
@@ -54,6 +57,7 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    prefetch_tmap(&tmC);
     for (int s = 0; s < G2_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -158,8 +162,50 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       tc_fence_after();
       const int row = tm * G2_BM + rank * 128 + q * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * G2_BN;
-      __nv_bfloat16* crow = p.C + static_cast<size_t>(row) * p.ldc + tn * G2_BN;
       const int ncols = min(G2_BN, p.N - tn * G2_BN);
+      if (!p.accumulate) {
+        // TMEM -> registers -> bf16 -> 128B-swizzled smem tile (32 rows x 64 cols) -> one TMA store per chunk: full-line
+        // writes, no per-thread global stores, M / N tails clipped by the tensor map
+        uint8_t* stage = epi_smem + (warp - 2) * 8192;
+        const int row0 = tm * G2_BM + rank * 128 + q * 32;
+#pragma unroll 1
+        for (int c = 0; c < G2_BN / 64; ++c) {
+          if (c * 64 >= ncols) break;
+          uint8_t* sbuf = stage + (c & 1) * 4096;
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32b_x32(taddr + c * 64, r0);
+          tmem_ld_32x32b_x32(taddr + c * 64 + 32, r1);
+          if (c >= 2) {  // the buffer is being reused: the TMA store issued two chunks ago must have read it
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+          }
+          tmem_ld_wait();
+          uint8_t* srow = sbuf + lane * 128;
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            const uint32_t* r = v < 4 ? r0 : r1;
+            const int e = (v & 3) * 8;
+            uint4 o;
+            o.x = pack_bf16(__uint_as_float(r[e + 0]), __uint_as_float(r[e + 1]));
+            o.y = pack_bf16(__uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
+            o.z = pack_bf16(__uint_as_float(r[e + 4]), __uint_as_float(r[e + 5]));
+            o.w = pack_bf16(__uint_as_float(r[e + 6]), __uint_as_float(r[e + 7]));
+            *reinterpret_cast<uint4*>(srow + ((v ^ (lane & 7)) << 4)) = o;  // 128B swizzle: 16-byte chunk index ^ (row % 8)
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, sbuf, tn * G2_BN + c * 64, row0);
+            tma_store_commit();
+          }
+        }
+        tc_fence_before();
+        mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[buf]), 0));  // accumulator drained: tell the leader
+        if (lane == 0) tma_store_wait_read<0>();  // staging buffers free before the next tile
+        __syncwarp();
+        continue;
+      }
+      __nv_bfloat16* crow = p.C + static_cast<size_t>(row) * p.ldc + tn * G2_BN;
 #pragma unroll 1
       for (int c = 0; c < G2_BN / 32; ++c) {
         if (c * 32 >= ncols) break;
@@ -175,7 +221,7 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
               float f[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[v * 8 + e]);
-              if (p.accumulate) {
+              {
                 uint4 old = *dst;
                 const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&old);
 #pragma unroll
@@ -194,8 +240,7 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             } else {
               for (int e = 0; e < 8; ++e) {
                 if (col + e < ncols) {
-                  float f = __uint_as_float(r[v * 8 + e]);
-                  if (p.accumulate) f += __bfloat162float(crow[col + e]);
+                  float f = __uint_as_float(r[v * 8 + e]) + __bfloat162float(crow[col + e]);
                   crow[col + e] = __float2bfloat16_rn(f);
                 }
               }
@@ -208,6 +253,7 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
   }
 
+  if (warp >= 2 && lane == 0) tma_store_wait<0>();  // all output tiles written before the CTA retires
   tc_fence_before();
   cluster_sync_all();
   if (warp == 1) {
@@ -217,7 +263,8 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 }
 
 template <int A_MN, int B_MN>
-static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm2Params& p, cudaStream_t stream) {
+static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const Gemm2Params& p,
+                        cudaStream_t stream) {
   auto kern = gemm_bf16_tcgen05_2sm<A_MN, B_MN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -244,7 +291,7 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  B200_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+  B200_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, p));
   return B200_OK;
 }
 
@@ -270,6 +317,9 @@ extern "C" int b200_gemm_bf16_2sm(const void* A, const void* B, void* C, int M, 
   else
     rc = make_tmap_2d_bf16(&tmB, B, K, N, ldb, 64, G2_BK);
   if (rc) return rc;
+  CUtensorMap tmC;  // output tile store: 64-column x 32-row boxes, 128B swizzle (N tails clipped by TMA)
+  rc = make_tmap_2d_bf16(&tmC, C, M, N, ldc, 64, 32);
+  if (rc) return rc;
   Gemm2Params p;
   p.C = reinterpret_cast<__nv_bfloat16*>(C);
   p.M = M;
@@ -283,8 +333,8 @@ extern "C" int b200_gemm_bf16_2sm(const void* A, const void* B, void* C, int M, 
   p.a_sbo = a_mn ? mn_sbo : k_sbo;
   p.b_lbo = b_mn ? mn_lbo : k_lbo;
   p.b_sbo = b_mn ? mn_sbo : k_sbo;
-  if (!a_mn && !b_mn) return launch_gemm2<0, 0>(tmA, tmB, p, stream);
-  if (!a_mn && b_mn) return launch_gemm2<0, 1>(tmA, tmB, p, stream);
-  if (a_mn && b_mn) return launch_gemm2<1, 1>(tmA, tmB, p, stream);
-  return launch_gemm2<1, 0>(tmA, tmB, p, stream);
+  if (!a_mn && !b_mn) return launch_gemm2<0, 0>(tmA, tmB, tmC, p, stream);
+  if (!a_mn && b_mn) return launch_gemm2<0, 1>(tmA, tmB, tmC, p, stream);
+  if (a_mn && b_mn) return launch_gemm2<1, 1>(tmA, tmB, tmC, p, stream);
+  return launch_gemm2<1, 0>(tmA, tmB, tmC, p, stream);
 }

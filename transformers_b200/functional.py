@@ -14,25 +14,55 @@ def _needs(ctx, i):
     return ctx.needs_input_grad[i]
 
 
+def _tp_reduce_async(t, group):
+    """Start an all-reduce(sum) of ``t`` on the communicator's stream; returns the work handle (None without a group)."""
+    if group is None:
+        return None
+    import torch.distributed as dist
+
+    return dist.all_reduce(t, group=group, async_op=True)
+
+
 class FusedLinearFn(torch.autograd.Function):
     """y = x @ cat(weights)^T  -- one GEMM for several nn.Linear layers that share their input
     (q/k/v: models/llama/modeling_llama.py:254-256; gate/up: :174-176) or a single one (o_proj, down_proj, lm_head).
 
     ``w_fused`` is the row-wise concatenation [sum(N_i), K] (maintained by the calling module); ``weights`` are the
-    individual parameters, passed so autograd routes their gradients; gradients are row-slices of one fused wgrad."""
+    individual parameters, passed so autograd routes their gradients; gradients are row-slices of one fused wgrad.
+
+    Tensor parallelism (``tp = (group, mode)``), collectives overlapped with our own GEMMs instead of the reference's
+    blocking DTensor redistributes (distributed/tensor_parallel.py:219-226, :320-328):
+      mode "col": the input gradient is a partial sum -> its all-reduce runs on the NCCL stream while the wgrad GEMM runs;
+      mode "row": the output is a partial sum -> the GEMM is issued in two row halves, the first half's all-reduce
+                  overlaps the second half's GEMM."""
 
     @staticmethod
-    def forward(ctx, x, w_fused, *weights):
+    def forward(ctx, x, w_fused, tp, *weights):
         K = x.shape[-1]
         x2 = x.reshape(-1, K)
         if not x2.is_contiguous():
             x2 = x2.contiguous()
         N = w_fused.shape[0]
-        y = torch.empty(*x.shape[:-1], N, device=x.device, dtype=x.dtype)  # returned as-is (not a view): a following
-        ops.gemm(x2, w_fused, out=y.view(-1, N))                             # all-reduce may update it in place
+        y = torch.empty(*x.shape[:-1], N, device=x.device, dtype=x.dtype)
+        y2 = y.view(-1, N)
+        group, mode = tp if tp is not None else (None, None)
+        T = x2.shape[0]
+        if group is not None and mode == "row" and T >= 512:
+            h = (T // 2 + 127) // 128 * 128
+            ops.gemm(x2[:h], w_fused, out=y2[:h])
+            w1 = _tp_reduce_async(y2[:h], group)
+            ops.gemm(x2[h:], w_fused, out=y2[h:])
+            w2 = _tp_reduce_async(y2[h:], group)
+            w1.wait()
+            w2.wait()
+        else:
+            ops.gemm(x2, w_fused, out=y2)
+            if group is not None and mode == "row":
+                _tp_reduce_async(y2, group).wait()
         ctx.save_for_backward(x2, w_fused)
         ctx.splits = [w.shape[0] for w in weights]
         ctx.x_shape = x.shape
+        ctx.tp = tp
         return y
 
     @staticmethod
@@ -42,18 +72,23 @@ class FusedLinearFn(torch.autograd.Function):
         dy2 = dy.reshape(-1, N)
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
-        dx = None
+        group, mode = ctx.tp if ctx.tp is not None else (None, None)
+        dx, work = None, None
         if _needs(ctx, 0):
             dx = ops.gemm(dy2, w_fused, b_mn=True).view(ctx.x_shape)  # dX = dY W : B stored [K'=N, N'=K]
+            if mode == "col":
+                work = _tp_reduce_async(dx, group)  # overlaps the wgrad GEMM below
         grads_w = [None] * len(ctx.splits)
-        if any(ctx.needs_input_grad[2:]):
+        if any(ctx.needs_input_grad[3:]):
             dw = ops.gemm(dy2, x2, a_mn=True, b_mn=True)  # dW[N,K] = dY^T X
             off = 0
             for i, n in enumerate(ctx.splits):
-                if ctx.needs_input_grad[2 + i]:
+                if ctx.needs_input_grad[3 + i]:
                     grads_w[i] = dw[off:off + n]
                 off += n
-        return (dx, None, *grads_w)
+        if work is not None:
+            work.wait()
+        return (dx, None, None, *grads_w)
 
 
 class RMSNormFn(torch.autograd.Function):
@@ -95,8 +130,9 @@ class QKVRopeAttentionFn(torch.autograd.Function):
     Backward: attention bwd writes dq|dk|dv straight into one packed buffer -> RoPE^T in place -> dgrad + wgrad GEMMs."""
 
     @staticmethod
-    def forward(ctx, x, w_fused, cos, sin, cfg, kv_start, kv_end, *weights):
+    def forward(ctx, x, w_fused, cos, sin, cfg, kv_start, kv_end, tp, *weights):
         Hq, Hkv, D, scale, causal, window, softcap = cfg
+        ctx.tp = tp
         B, S, K = x.shape
         x2 = x.reshape(B * S, K)
         if not x2.is_contiguous():
@@ -134,15 +170,18 @@ class QKVRopeAttentionFn(torch.autograd.Function):
         ops.rope_(dqkv, cos, sin, Hq + Hkv, D, backward=True)
         d2 = dqkv.view(B * S, W)
         dx = ops.gemm(d2, w_fused, b_mn=True).view(ctx.x_shape) if _needs(ctx, 0) else None
+        work = _tp_reduce_async(dx, ctx.tp[0]) if (dx is not None and ctx.tp is not None) else None  # overlaps the wgrad
         grads_w = [None] * len(ctx.splits)
-        if any(ctx.needs_input_grad[7:]):
+        if any(ctx.needs_input_grad[8:]):
             dw = ops.gemm(d2, x2, a_mn=True, b_mn=True)
             off = 0
             for i, n in enumerate(ctx.splits):
-                if ctx.needs_input_grad[7 + i]:
+                if ctx.needs_input_grad[8 + i]:
                     grads_w[i] = dw[off:off + n]
                 off += n
-        return (dx, None, None, None, None, None, None, *grads_w)
+        if work is not None:
+            work.wait()
+        return (dx, None, None, None, None, None, None, None, *grads_w)
 
 
 class FlashAttentionFn(torch.autograd.Function):
@@ -175,7 +214,8 @@ class QKVRopeFn(torch.autograd.Function):
     through Cache.update, models/llama/modeling_llama.py:262, and attention runs through the registry entry)."""
 
     @staticmethod
-    def forward(ctx, x, w_fused, cos, sin, n_rot, D, *weights):
+    def forward(ctx, x, w_fused, cos, sin, n_rot, D, tp, *weights):
+        ctx.tp = tp
         B, S, K = x.shape
         x2 = x.reshape(B * S, K)
         if not x2.is_contiguous():
@@ -196,15 +236,18 @@ class QKVRopeFn(torch.autograd.Function):
         ops.rope_(dqkv, cos, sin, *ctx.cfg, backward=True)
         d2 = dqkv.view(B * S, -1)
         dx = ops.gemm(d2, w_fused, b_mn=True).view(ctx.x_shape) if _needs(ctx, 0) else None
+        work = _tp_reduce_async(dx, ctx.tp[0]) if (dx is not None and ctx.tp is not None) else None
         grads_w = [None] * len(ctx.splits)
-        if any(ctx.needs_input_grad[6:]):
+        if any(ctx.needs_input_grad[7:]):
             dw = ops.gemm(d2, x2, a_mn=True, b_mn=True)
             off = 0
             for i, n in enumerate(ctx.splits):
-                if ctx.needs_input_grad[6 + i]:
+                if ctx.needs_input_grad[7 + i]:
                     grads_w[i] = dw[off:off + n]
                 off += n
-        return (dx, None, None, None, None, None, *grads_w)
+        if work is not None:
+            work.wait()
+        return (dx, None, None, None, None, None, None, *grads_w)
 
 
 class EmbeddingFn(torch.autograd.Function):

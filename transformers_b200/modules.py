@@ -80,18 +80,19 @@ class B200RMSNormMixin:
 
 class B200MLPMixin:
     def forward(self, x):  # LlamaMLP.forward models/llama/modeling_llama.py:174-176
-        x = _tp_copy(self, x)
         if not x.is_cuda:
-            return _tp_allreduce(self, super().forward(x))
+            return _tp_allreduce(self, super().forward(_tp_copy(self, x)))
+        group = self.__dict__.get("_b200_tp_group")
+        col = (group, "col") if group is not None else None
+        row = (group, "row") if group is not None else None
         _check_no_bias(self.gate_proj, self.up_proj, self.down_proj)
         wg, wu, wd = _local(self.gate_proj.weight), _local(self.up_proj.weight), _local(self.down_proj.weight)
         act = getattr(self.config, "hidden_act", None) or getattr(self.config, "hidden_activation", "silu")
         if act not in ("silu", "gelu_pytorch_tanh"):
             raise B200Error(f"transformers_b200: activation {act} not supported")
-        gu = Fn.FusedLinearFn.apply(x, fused_weight(self, "gate_up", [wg, wu]), wg, wu)
+        gu = Fn.FusedLinearFn.apply(x, fused_weight(self, "gate_up", [wg, wu]), col, wg, wu)
         h = Fn.GluFn.apply(gu, act == "gelu_pytorch_tanh")
-        out = Fn.FusedLinearFn.apply(h, fused_weight(self, "down", [wd]), wd)
-        return _tp_allreduce(self, out)
+        return Fn.FusedLinearFn.apply(h, fused_weight(self, "down", [wd]), row, wd)  # row mode: all-reduce inside, overlapped
 
 
 class B200AttentionMixin:
@@ -103,11 +104,13 @@ class B200AttentionMixin:
         return getattr(self.config, "sliding_window", None)  # Mistral (modeling_mistral.py:172); Llama: None
 
     def forward(self, hidden_states, position_embeddings=None, attention_mask=None, past_key_values=None, **kwargs):
-        hidden_states = _tp_copy(self, hidden_states)
         if self.config._attn_implementation != ATTN_NAME or not hidden_states.is_cuda:
-            out, w = super().forward(hidden_states, position_embeddings=position_embeddings, attention_mask=attention_mask,
-                                     past_key_values=past_key_values, **kwargs)
+            out, w = super().forward(_tp_copy(self, hidden_states), position_embeddings=position_embeddings,
+                                     attention_mask=attention_mask, past_key_values=past_key_values, **kwargs)
             return _tp_allreduce(self, out), w
+        group = self.__dict__.get("_b200_tp_group")
+        col = (group, "col") if group is not None else None
+        row = (group, "row") if group is not None else None
         _check_no_bias(self.q_proj, self.k_proj, self.v_proj, self.o_proj)
         if self.training and getattr(self, "attention_dropout", 0.0):
             raise B200Error("transformers_b200: attention dropout is not supported")
@@ -123,11 +126,11 @@ class B200AttentionMixin:
         if past_key_values is None:
             kv_start, kv_end = mask_to_kv_ranges(attention_mask)
             cfg = (Hq, Hkv, D, float(self.scaling), True, int(window), float(softcap))
-            attn = Fn.QKVRopeAttentionFn.apply(hidden_states, wqkv, cos, sin, cfg, kv_start, kv_end, wq, wk, wv)
+            attn = Fn.QKVRopeAttentionFn.apply(hidden_states, wqkv, cos, sin, cfg, kv_start, kv_end, col, wq, wk, wv)
         else:
             from .integration import b200_attention_forward
 
-            qkv = Fn.QKVRopeFn.apply(hidden_states, wqkv, cos, sin, Hq + Hkv, D, wq, wk, wv)
+            qkv = Fn.QKVRopeFn.apply(hidden_states, wqkv, cos, sin, Hq + Hkv, D, col, wq, wk, wv)
             q = qkv[..., : Hq * D].view(B, S, Hq, D).transpose(1, 2)
             k = qkv[..., Hq * D:(Hq + Hkv) * D].view(B, S, Hkv, D).transpose(1, 2)
             v = qkv[..., (Hq + Hkv) * D:].view(B, S, Hkv, D).transpose(1, 2)
@@ -135,8 +138,8 @@ class B200AttentionMixin:
             attn, _ = b200_attention_forward(self, q, k, v, attention_mask, dropout=0.0, scaling=self.scaling,
                                              sliding_window=window or None, softcap=softcap or None, **kwargs)
             attn = attn.reshape(B, S, Hq * D)
-        out = Fn.FusedLinearFn.apply(attn, fused_weight(self, "o", [wo]), wo)
-        return _tp_allreduce(self, out), None
+        out = Fn.FusedLinearFn.apply(attn, fused_weight(self, "o", [wo]), row, wo)  # row mode: all-reduce inside, overlapped
+        return out, None
 
 
 class B200EmbeddingMixin:
@@ -156,12 +159,11 @@ class B200LinearMixin:
     def forward(self, x):
         w = _local(self.weight)
         gather = self.__dict__.get("_b200_tp_gather", False)
-        if gather:
-            x = _tp_copy(self, x)
         if not w.is_cuda or self.bias is not None:
-            y = super().forward(x)
+            y = super().forward(_tp_copy(self, x) if gather else x)
         else:
-            y = Fn.FusedLinearFn.apply(x, fused_weight(self, "w", [w]), w)
+            col = (self.__dict__["_b200_tp_group"], "col") if gather else None
+            y = Fn.FusedLinearFn.apply(x, fused_weight(self, "w", [w]), col, w)
         if gather:
             from .parallel import gather_last_dim
 
