@@ -28,6 +28,12 @@ LLAMA3_8B = dict(vocab_size=128256, hidden_size=4096, intermediate_size=14336, n
 FLOPS_PER_TOKEN_FWD_BWD = 48.249e9  # BASELINE.md §2 (2mnk per GEMM, causal attention at half, bwd = 2x fwd)
 
 
+def workload_name(world: int, batch: int, seq: int) -> str:
+    if world == 1:
+        return f"Llama-3-8B bf16 forward+backward seq={seq} batch={batch} on 1xB200 (configs[1])"
+    return f"Llama-3-8B bf16 forward+backward seq={seq} batch={batch}, tp_plan across {world}xB200 (configs[2])"
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -153,9 +159,11 @@ def run_reference(args):
     value = seq / (LLAMA3_8B["num_hidden_layers"] * t_layer)
     line = {
         "impl": "reference", "metric": "tokens/sec Llama-3-8B fwd+bwd seq4096", "value": value, "unit": "tokens/s",
-        "n_gpus": args.gpus, "steps": len(times), "warmup": 1, "ms_per_step": t_layer * 1e3 * LLAMA3_8B["num_hidden_layers"] * (args.batch * args.seq / seq),
+        "n_gpus": args.gpus, "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": t_layer * 1e3 * LLAMA3_8B["num_hidden_layers"] * (args.batch * args.seq / seq),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "Llama-3-8B bf16 forward+backward seq=4096 batch=4 (reference eager path on host CPU, bounded sample)"},
+        "config": {"workload": workload_name(max(1, args.gpus), args.batch, args.seq), "model": "Llama-3-8B (random init)",
+                   "global_batch": args.batch, "seq_len": args.seq,
+                   "note": "reference eager path (oracle port) on the host CPU cores, bounded sample extrapolated per layer"},
         "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": threads, "kind": "port",
                          "sample": f"1 full-width decoder layer fwd+bwd B=1 S={seq} x{len(times)}: {t_layer:.2f} s each; tokens/s = S/(32*t_layer)"},
         "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -319,8 +327,7 @@ def run_b200(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak" if parallelism == "dp" and world > 1 else "strong", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": (f"Llama-3-8B bf16 forward+backward seq={S} batch={B} on 1xB200 (configs[1])" if world == 1 else
-                                    f"Llama-3-8B bf16 forward+backward seq={S} batch={B}, tp_plan across {world}xB200 (configs[2])") if args.layers == 32
+            "config": {"workload": workload_name(world, B, S) if args.layers == 32
                        else f"DEBUG {args.layers}-layer model -- not the named config", "model": "Llama-3-8B (random init)",
                        "global_batch": B * replicas, "seq_len": S, "parallelism": f"{parallelism}{world}" if world > 1 else "single",
                        "l2": "working set (16 GB weights + activations) >> 126 MB L2; no explicit flush needed",
