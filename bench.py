@@ -34,6 +34,23 @@ def workload_name(world: int, batch: int, seq: int) -> str:
     return f"Llama-3-8B bf16 forward+backward seq={seq} batch={batch}, tp_plan across {world}xB200 (configs[2])"
 
 
+def ncu_gemm_traffic():
+    """DRAM bytes (read + write) per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/r01_ncu_summary_final.csv: gate|up fwd, dgrad and wgrad GEMMs at the Llama-3-8B shapes); None if absent."""
+    import csv
+
+    path = os.path.join(ROOT, "profiles", "r01_ncu_summary_final.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], rows[1]
+        ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        vals = [float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]] for r in rows[2:] if "gemm_bf16_tcgen05" in r[ik]]
+        return (sum(vals) / len(vals)) if vals else None
+    except Exception:
+        return None
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -147,7 +164,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    torch.set_num_threads(os.cpu_count() or 1)
+    # torch's default intra-op pool (= physical cores on the GPU box): forcing os.cpu_count() hyper-threads measured 7x
+    # slower (9.65 s vs 1.35 s per layer on the 64-core / 128-thread host), which would flatter the GPU arm
     seq = 1024
     for _ in range(args.warmup if args.warmup < 2 else 1):
         cpu_reference_sample(seq, repeats=0)
@@ -340,7 +358,10 @@ def run_b200(args):
             "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tcgen05 (all nn.Linear fwd/dgrad/wgrad launches of one step)",
                          "achieved": gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": (gemm_fl / (gemm_ms * 1e-3) / 1e12 / peak_tf) if gemm_ms else None, "peak_source": peak_src,
-                         "traffic": None, "share_of_step": gemm_ms / ours_ms if ours_ms else None,
+                         "traffic": ncu_gemm_traffic(),
+                         "traffic_note": "mean DRAM read+write bytes per launch over the 16384x28672x4096 fwd / dgrad / wgrad GEMMs of "
+                                         "profiles/r01_ncu_summary_final.csv (algorithmic: 1.31 GB each)",
+                         "share_of_step": gemm_ms / ours_ms if ours_ms else None,
                          "whole_step_frac": per_gpu_tf / peak_tf},
             "kernels_ms": {k: {"ms": round(v[0], 3), "launches": v[1]} for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])},
         }
