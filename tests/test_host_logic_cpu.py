@@ -1,0 +1,64 @@
+"""Host-side logic that needs no kernels: padding-mask -> kv range conversion, fused-weight cache invalidation,
+tp_plan resolution / sharding shapes, C-ABI argument validation (errno-style codes before any launch)."""
+import pytest
+import torch
+
+from _hf import import_transformers
+
+tf = import_transformers()
+
+
+def test_mask_to_kv_ranges_left_right_and_full():
+    from transformers_b200.modules import mask_to_kv_ranges
+
+    assert mask_to_kv_ranges(None) == (None, None)
+    m = torch.tensor([[1, 1, 1, 1, 0, 0], [0, 0, 1, 1, 1, 1], [1, 1, 1, 1, 1, 1], [0, 1, 1, 1, 0, 0]])
+    s, e = mask_to_kv_ranges(m)
+    assert s.tolist() == [0, 2, 0, 1] and e.tolist() == [4, 6, 6, 4]
+    assert s.dtype == torch.int32 and e.dtype == torch.int32
+    from transformers_b200 import B200Error
+
+    with pytest.raises(B200Error):
+        mask_to_kv_ranges(torch.ones(2, 1, 4, 4))  # 4-D (eager-style) masks are not what the b200 mask entry produces
+
+
+def test_fused_weight_cache_tracks_parameter_updates():
+    from transformers_b200.modules import fused_weight
+
+    mod = torch.nn.Module()
+    a = torch.nn.Parameter(torch.randn(4, 8))
+    b = torch.nn.Parameter(torch.randn(2, 8))
+    f1 = fused_weight(mod, "ab", [a, b])
+    assert f1.shape == (6, 8) and torch.equal(f1[:4], a) and torch.equal(f1[4:], b)
+    assert fused_weight(mod, "ab", [a, b]) is f1  # cache hit
+    with torch.no_grad():
+        a.add_(1.0)  # optimizer-style in-place update bumps _version
+    f2 = fused_weight(mod, "ab", [a, b])
+    assert f2 is not f1 and torch.equal(f2[:4], a)
+    c = torch.nn.Parameter(torch.randn(4, 8))
+    assert torch.equal(fused_weight(mod, "ab", [c, b])[:4], c)  # replaced parameter object
+    assert fused_weight(mod, "single", [a]) is a.data or fused_weight(mod, "single", [a]).data_ptr() == a.data_ptr()
+
+
+def test_resolve_plan_reads_the_reference_tp_plan():
+    from transformers_b200.parallel import resolve_plan
+
+    cfg = tf.LlamaConfig(vocab_size=64, hidden_size=32, intermediate_size=64, num_hidden_layers=1, num_attention_heads=4,
+                         num_key_value_heads=2, head_dim=8)
+    model = tf.LlamaForCausalLM._from_config(cfg, attn_implementation="eager")
+    plan = resolve_plan(model)
+    assert plan["model.layers.*.self_attn.q_proj"] == "colwise" and plan["model.layers.*.self_attn.o_proj"] == "rowwise"
+    assert plan["model.layers.*.mlp.down_proj"] == "rowwise" and plan["lm_head"] == "colwise_gather_output"
+
+
+def test_c_abi_validates_arguments_without_a_gpu():
+    from transformers_b200 import _lib
+
+    lib = _lib.load()
+    assert lib.b200_rmsnorm_fwd(None, None, None, None, None, None, 4, 7, 1e-5, 0, None) == -22  # H % 8
+    assert "multiple of 8" in _lib.last_error()
+    assert lib.b200_rope(None, None, None, 1, 4, 2, 24, 64, 1, 0, None) == -22  # head_dim % 16
+    assert lib.b200_kv_append(None, None, None, None, 1, 1, 4, 64, 8, 8, 8, 8, 8, 8, 8, 8, 8, 10, 12, None) == -22  # over capacity
+    assert lib.b200_attn_fwd(None, None, None, None, None, 128, 1, 8, 8, 4, 3, 128, *([8] * 12), 1.0, 0.0, 1, 0, None, None, None) == -22
+    assert "multiple of Hkv" in _lib.last_error()
+    assert lib.b200_moe_route(None, None, None, None, None, None, 4, 2, 0, None) == -22

@@ -26,7 +26,6 @@ def check(rc: int, what: str) -> None:
 
 
 _LAUNCHES = 0  # kernels launched through the C-ABI by this process (bench.py reports it as gpu_launches)
-_TIMER = None  # optional callable(name) -> context manager, installed by bench.py for the per-kernel breakdown
 
 
 def launch_count() -> int:
