@@ -9,6 +9,8 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
 namespace b200 {
 
 constexpr int G2_BM = 256;        // per cluster
@@ -327,7 +329,14 @@ extern "C" int b200_gemm_bf16_2sm(const void* A, const void* B, void* C, int M, 
   p.K = K;
   p.ldc = ldc;
   p.accumulate = accumulate;
-  p.group_m = 8;
+  // M tiles per rasterisation group (wave footprint ~ group_m x 74/group_m tiles of 256x256).  B200_GEMM2_GROUP_M overrides the
+  // default for sweeps (profiles/README.md: DRAM re-reads are the open issue of this kernel).
+  static const int group_m_env = [] {
+    const char* e = getenv("B200_GEMM2_GROUP_M");
+    const int v = e ? atoi(e) : 0;
+    return v > 0 && v <= 64 ? v : 8;
+  }();
+  p.group_m = group_m_env;
   const uint32_t k_lbo = 16, k_sbo = 1024, mn_lbo = 64 * G2_BK * 2, mn_sbo = 1024;
   p.a_lbo = a_mn ? mn_lbo : k_lbo;
   p.a_sbo = a_mn ? mn_sbo : k_sbo;
