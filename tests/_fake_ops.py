@@ -1,0 +1,224 @@
+"""Test-only stand-ins for ``transformers_b200.ops`` so the HOST logic of the kernel path (autograd Functions, fused-weight
+handling, tensor-parallel chunking / overlap, shapes and strides handed to the kernels) can run on CPU tensors.
+
+Each function restates the contract documented in ``transformers_b200/ops.py`` with plain torch in the operand dtype
+(fp32 in the tests).  ``install()`` swaps them in for the current process only; nothing in the product imports this file,
+and the product keeps failing loudly without the CUDA library (tests/test_plugin_cpu.py).
+"""
+import torch
+import torch.nn.functional as F
+
+CALLS = []  # (name, shapes) log so tests can assert what the host logic launched
+
+
+def _log(name, *ts):
+    CALLS.append((name, tuple(tuple(t.shape) for t in ts if t is not None)))
+
+
+def gemm(a, b, *, a_mn=False, b_mn=False, out=None, accumulate=False):
+    assert a.dim() == 2 and b.dim() == 2
+    assert a.stride(1) == 1 or a.shape[1] == 1, "gemm A needs a unit inner stride"
+    assert b.stride(1) == 1 or b.shape[1] == 1, "gemm B needs a unit inner stride"
+    A = a.t() if a_mn else a
+    Bm = b if b_mn else b.t()
+    r = A @ Bm
+    _log("gemm", a, b)
+    if out is None:
+        assert not accumulate
+        return r
+    assert out.shape == r.shape and out.stride(1) == 1
+    if accumulate:
+        out += r
+    else:
+        out.copy_(r)
+    return out
+
+
+def embedding_fwd(ids, weight, scale=None):
+    y = F.embedding(ids, weight)
+    _log("embedding_fwd", ids)
+    return y * torch.tensor(scale, dtype=weight.dtype) if scale is not None else y
+
+
+def embedding_bwd(ids, dout, num_embeddings, padding_idx, scale=None):
+    H = dout.shape[-1]
+    d = dout.reshape(-1, H)
+    if scale is not None:
+        d = d * torch.tensor(scale, dtype=d.dtype)
+    dw = torch.zeros(num_embeddings, H, dtype=dout.dtype)
+    dw.index_add_(0, ids.reshape(-1), d)
+    if padding_idx is not None:
+        dw[padding_idx] = 0
+    _log("embedding_bwd", ids)
+    return dw
+
+
+def rmsnorm_fwd(x, weight, eps, gemma=False, residual=None):
+    r = x if residual is None else x + residual
+    rf = r.float()
+    rstd = torch.rsqrt(rf.pow(2).mean(-1) + eps)
+    wv = (1.0 + weight.float()) if gemma else weight.float()
+    y = (rf * rstd[..., None] * wv).to(x.dtype)
+    _log("rmsnorm_fwd", x)
+    return y, rstd.reshape(-1), (r if residual is not None else None)
+
+
+def rmsnorm_bwd(dy, x, weight, rstd, gemma=False):
+    H = x.shape[-1]
+    xf, dyf = x.reshape(-1, H).float(), dy.reshape(-1, H).float()
+    wv = (1.0 + weight.float()) if gemma else weight.float()
+    xhat = xf * rstd[:, None]
+    g = dyf * wv
+    dx = rstd[:, None] * (g - xhat * (g * xhat).mean(-1, keepdim=True))
+    dw = (dyf * xhat).sum(0)
+    _log("rmsnorm_bwd", x)
+    return dx.to(x.dtype).view(x.shape), dw.to(weight.dtype)
+
+
+def rope_(qkv, cos, sin, n_rot_heads, head_dim, backward=False):
+    B, S, W = qkv.shape
+    assert qkv.is_contiguous()
+    D, h = head_dim, head_dim // 2
+    x = qkv[..., : n_rot_heads * D].reshape(B, S, n_rot_heads, D)
+    c = cos.reshape(-1, S, 1, D)
+    s = sin.reshape(-1, S, 1, D)
+    if not backward:
+        rot = torch.cat([-x[..., h:], x[..., :h]], -1)
+        y = x * c + rot * s
+    else:
+        z = x * s
+        y = x * c + torch.cat([z[..., h:], -z[..., :h]], -1)
+    qkv[..., : n_rot_heads * D] = y.reshape(B, S, n_rot_heads * D)
+    _log("rope_", qkv)
+    return qkv
+
+
+def _act(g, gelu):
+    return F.gelu(g, approximate="tanh") if gelu else F.silu(g)
+
+
+def glu_fwd(gu, gelu=False):
+    I = gu.shape[-1] // 2
+    _log("glu_fwd", gu)
+    return _act(gu[..., :I], gelu) * gu[..., I:]
+
+
+def glu_bwd(dh, gu, gelu=False):
+    with torch.enable_grad():
+        g = gu.detach().clone().requires_grad_(True)
+        I = g.shape[-1] // 2
+        y = _act(g[..., :I], gelu) * g[..., I:]
+        (dgu,) = torch.autograd.grad(y, g, dh.reshape(y.shape))
+    _log("glu_bwd", gu)
+    return dgu
+
+
+def _attn_math(q, k, v, scale, causal, window, softcap, kv_start, kv_end):
+    B, Sq, Hq, D = q.shape
+    Skv, Hkv = k.shape[1], k.shape[2]
+    rep = Hq // Hkv
+    qf = q.permute(0, 2, 1, 3).double()
+    kf = k.permute(0, 2, 1, 3).repeat_interleave(rep, 1).double()
+    vf = v.permute(0, 2, 1, 3).repeat_interleave(rep, 1).double()
+    s = qf @ kf.transpose(-1, -2) * scale
+    if softcap:
+        s = softcap * torch.tanh(s / softcap)
+    qpos = torch.arange(Sq) + (Skv - Sq)  # bottom-right aligned
+    kidx = torch.arange(Skv)
+    m = torch.ones(Sq, Skv, dtype=torch.bool)
+    if causal:
+        m &= kidx[None, :] <= qpos[:, None]
+    if window:
+        m &= kidx[None, :] > qpos[:, None] - window
+    m = m[None, None].expand(B, 1, Sq, Skv)
+    if kv_start is not None:
+        m = m & (kidx[None, None, None, :] >= kv_start.long()[:, None, None, None])
+    if kv_end is not None:
+        m = m & (kidx[None, None, None, :] < kv_end.long()[:, None, None, None])
+    s = s.masked_fill(~m, float("-inf"))
+    lse = torch.logsumexp(s, -1)
+    p = torch.exp(s - lse[..., None])
+    p = torch.nan_to_num(p, nan=0.0)  # fully masked rows -> zeros
+    out = (p @ vf).permute(0, 2, 1, 3)
+    return out, lse
+
+
+def attn_fwd(q, k, v, *, scale, causal, window=0, softcap=0.0, kv_start=None, kv_end=None, out=None):
+    for t in (q, k, v):
+        assert t.dim() == 4 and t.stride(3) == 1, "attention operands: [B,S,h,D] views with unit stride on D"
+    o, lse = _attn_math(q, k, v, scale, causal, window, softcap, kv_start, kv_end)
+    B, Sq, Hq, _ = q.shape
+    ls = (Sq + 127) // 128 * 128
+    lse_p = torch.zeros(B, Hq, ls, dtype=torch.float32)
+    lse_p[..., :Sq] = lse.float()
+    o = o.to(q.dtype).contiguous()
+    if out is not None:
+        out.copy_(o)
+        o = out
+    _log("attn_fwd", q, k, v)
+    return o, lse_p
+
+
+def attn_bwd(q, k, v, out, dout, lse, dq, dk, dv, *, scale, causal, window=0, softcap=0.0, kv_start=None, kv_end=None):
+    for t in (q, k, v, out, dout, dq, dk, dv):
+        assert t.stride(3) == 1
+    with torch.enable_grad():
+        qq, kk, vv = (t.detach().clone().requires_grad_(True) for t in (q, k, v))
+        o, _ = _attn_math(qq, kk, vv, scale, causal, window, softcap, kv_start, kv_end)
+        gq, gk, gv = torch.autograd.grad(o, (qq, kk, vv), dout.double())
+    dq.copy_(gq.to(dq.dtype))
+    dk.copy_(gk.to(dk.dtype))
+    dv.copy_(gv.to(dv.dtype))
+    _log("attn_bwd", q, k, v)
+    return dq, dk, dv
+
+
+def _ce_targets(labels, B, S, shift, ignore_index):
+    labels = labels.reshape(B, S)
+    if shift:
+        tgt = torch.full_like(labels, ignore_index)
+        tgt[:, :-1] = labels[:, 1:]
+    else:
+        tgt = labels
+    return tgt.reshape(-1)
+
+
+def ce_fwd(logits, labels, shift=True, ignore_index=-100, num_items=None):
+    B, S, V = logits.shape
+    tgt = _ce_targets(labels, B, S, shift, ignore_index)
+    lg = logits.reshape(B * S, V).float()
+    lse = torch.logsumexp(lg, -1)
+    valid = tgt != ignore_index
+    nll = (lse - lg.gather(1, tgt.clamp(min=0)[:, None])[:, 0]) * valid
+    denom = torch.tensor([float(num_items) if num_items else float(valid.sum())])
+    _log("ce_fwd", logits)
+    return (nll.sum() / denom[0]).to(torch.float32), lse, denom
+
+
+def ce_bwd(logits, labels, lse, dloss, denom, shift=True, ignore_index=-100):
+    B, S, V = logits.shape
+    tgt = _ce_targets(labels, B, S, shift, ignore_index)
+    lg = logits.reshape(B * S, V).float()
+    p = torch.exp(lg - lse[:, None])
+    valid = tgt != ignore_index
+    p[torch.arange(B * S)[valid], tgt[valid]] -= 1.0
+    p = p * valid[:, None] * (dloss.reshape(()).float() / denom[0])
+    _log("ce_bwd", logits)
+    return p.to(logits.dtype).view(B, S, V)
+
+
+_NAMES = ["gemm", "embedding_fwd", "embedding_bwd", "rmsnorm_fwd", "rmsnorm_bwd", "rope_", "glu_fwd", "glu_bwd", "attn_fwd",
+          "attn_bwd", "ce_fwd", "ce_bwd"]
+
+
+def install(setattr_fn=setattr):
+    """Swap the fakes in (process-local).  ``setattr_fn`` may be pytest's ``monkeypatch.setattr`` so the swap is undone."""
+    import transformers_b200.modules as M
+    import transformers_b200.ops as ops
+
+    g = globals()
+    for n in _NAMES:
+        setattr_fn(ops, n, g[n])
+    setattr_fn(M, "_on_b200", lambda t: True)
+    setattr_fn(M, "KERNEL_DTYPES", (torch.bfloat16, torch.float32))
+    CALLS.clear()

@@ -1,0 +1,141 @@
+"""The kernel path's HOST logic on CPU: the real ``functional.py`` / ``modules.py`` / ``integration.py`` code runs, with the
+C-ABI calls replaced by the torch stand-ins of ``tests/_fake_ops.py``.  What is under test is everything between the
+reference's module boundary and the kernel launches: fused-weight packing, the strided q/k/v views handed to attention, RoPE
+on the packed buffer, gradient routing to the individual q/k/v / gate/up parameters, mask -> kv range conversion, the loss
+hook.  (The kernels themselves are tested against the oracle in tests/test_kernels_gpu.py / test_model_gpu.py.)
+
+Reference for the numbers: the stock eager forward/backward of the same model in the same process (fp32)."""
+import copy
+
+import pytest
+import torch
+
+import _fake_ops
+from _hf import import_transformers
+
+transformers = import_transformers()
+import transformers_b200  # noqa: E402
+
+
+@pytest.fixture(autouse=True)
+def _fakes(monkeypatch):
+    transformers_b200.enable()
+    _fake_ops.install(monkeypatch.setattr)
+    yield
+
+
+def _llama_cfg(**kw):
+    base = dict(vocab_size=160, hidden_size=64, intermediate_size=176, num_hidden_layers=2, num_attention_heads=4,
+                num_key_value_heads=2, head_dim=16, rms_norm_eps=1e-5, max_position_embeddings=128,
+                rope_parameters={"rope_type": "default", "rope_theta": 500000.0})
+    base.update(kw)
+    return transformers.LlamaConfig(**base)
+
+
+def _pair(cls, cfg):
+    """(stock eager model, accelerated copy on the faked kernel path) with identical weights."""
+    from transformers.monkey_patching import clear_patch_mapping
+
+    import transformers_b200.integration as integ
+
+    clear_patch_mapping()
+    try:
+        transformers.set_seed(0)
+        ref = cls._from_config(cfg, attn_implementation="eager", dtype=torch.float32)
+    finally:
+        integ._enabled = False
+        transformers_b200.enable()
+    ours = copy.deepcopy(ref)
+    transformers_b200.accelerate(ours)
+    return ref, ours
+
+
+def _compare(ref, ours, ids, attention_mask=None, atol=2e-5):
+    kw = dict(input_ids=ids, labels=ids, use_cache=False)
+    if attention_mask is not None:
+        kw["attention_mask"] = attention_mask
+        keep = attention_mask.bool()
+        keep[:, 1:] &= attention_mask.bool()[:, :-1]  # a target predicted FROM a pad position is garbage in both paths
+        kw["labels"] = ids.masked_fill(~keep, -100)
+    a = ref(**kw)
+    a.loss.backward()
+    _fake_ops.CALLS.clear()
+    b = ours(**kw)
+    b.loss.backward()
+    valid = slice(None) if attention_mask is None else attention_mask.bool()
+    torch.testing.assert_close(b.logits[valid], a.logits[valid], atol=atol, rtol=1e-4)
+    torch.testing.assert_close(b.loss, a.loss, atol=1e-5, rtol=1e-5)
+    ga = dict(ref.named_parameters())
+    for n, p in ours.named_parameters():
+        assert p.grad is not None, n
+        torch.testing.assert_close(p.grad, ga[n].grad, atol=atol, rtol=1e-3, msg=lambda m, n=n: f"{n}: {m}")
+
+
+def test_llama_fwd_bwd_through_kernel_path_host_logic():
+    ref, ours = _pair(transformers.LlamaForCausalLM, _llama_cfg())
+    torch.manual_seed(1)
+    ids = torch.randint(0, 160, (2, 24))
+    _compare(ref, ours, ids)
+    names = [c[0] for c in _fake_ops.CALLS]
+    # per layer: qkv GEMM + o GEMM + gate|up GEMM + down GEMM forward (4), one attention, one GLU; + lm_head
+    assert names.count("attn_fwd") == 2 and names.count("attn_bwd") == 2
+    assert names.count("glu_fwd") == 2 and names.count("rope_") == 4
+    assert names.count("gemm") == 3 * (4 * 2 + 1)  # fwd + dgrad + wgrad for each fused linear
+    assert names.count("ce_fwd") == 1 and names.count("embedding_bwd") == 1
+
+
+def test_llama_left_and_right_padding():
+    ref, ours = _pair(transformers.LlamaForCausalLM, _llama_cfg())
+    torch.manual_seed(2)
+    ids = torch.randint(0, 160, (3, 20))
+    am = torch.ones(3, 20, dtype=torch.long)
+    am[0, :5] = 0   # left padded
+    am[1, -4:] = 0  # right padded
+    _compare(ref, ours, ids, am)
+
+
+def test_mistral_sliding_window():
+    cfg = transformers.MistralConfig(vocab_size=160, hidden_size=64, intermediate_size=176, num_hidden_layers=2,
+                                     num_attention_heads=4, num_key_value_heads=2, head_dim=16, sliding_window=8,
+                                     max_position_embeddings=128)
+    ref, ours = _pair(transformers.MistralForCausalLM, cfg)
+    torch.manual_seed(3)
+    _compare(ref, ours, torch.randint(0, 160, (2, 32)))
+
+
+def test_gemma2_softcap_scaled_embedding_and_alternating_window():
+    cfg = transformers.Gemma2Config(vocab_size=160, hidden_size=64, intermediate_size=176, num_hidden_layers=2,
+                                    num_attention_heads=4, num_key_value_heads=2, head_dim=16, sliding_window=8,
+                                    query_pre_attn_scalar=16, max_position_embeddings=128, pad_token_id=0)
+    ref, ours = _pair(transformers.Gemma2ForCausalLM, cfg)
+    torch.manual_seed(4)
+    ids = torch.randint(1, 160, (2, 24))
+    _compare(ref, ours, ids, atol=5e-5)
+    assert ours.loss_function is not transformers_b200.integration.b200_causal_lm_loss  # final softcapping: stock loss stays
+
+
+def test_kv_cache_path_matches_full_forward():
+    """generate()-style prefill + one-token steps through QKVRopeFn + Cache.update + the registry entry."""
+    ref, ours = _pair(transformers.LlamaForCausalLM, _llama_cfg())
+    ours.eval()
+    ref.eval()
+    torch.manual_seed(5)
+    ids = torch.randint(0, 160, (2, 12))
+    with torch.no_grad():
+        full = ref(input_ids=ids).logits
+        cache = transformers.DynamicCache(config=ours.config)
+        out = ours(input_ids=ids[:, :8], past_key_values=cache, use_cache=True)
+        steps = [out.logits]
+        for t in range(8, 12):
+            out = ours(input_ids=ids[:, t:t + 1], past_key_values=cache, use_cache=True)
+            steps.append(out.logits)
+    torch.testing.assert_close(torch.cat(steps, 1), full, atol=2e-5, rtol=1e-4)
+
+
+def test_gradient_checkpointing_replays_functions():
+    ref, ours = _pair(transformers.LlamaForCausalLM, _llama_cfg())
+    ours.train()
+    ref.train()
+    ours.gradient_checkpointing_enable()
+    torch.manual_seed(6)
+    _compare(ref, ours, torch.randint(0, 160, (2, 16)))

@@ -153,7 +153,7 @@ def b200_causal_lm_loss(logits, labels, vocab_size=None, num_items_in_batch=None
         labels, shift = shift_labels, False
     else:
         shift = True
-    if not logits.is_cuda or logits.dtype != torch.bfloat16:
+    if not M._on_b200(logits) or logits.dtype not in M.KERNEL_DTYPES:
         raise B200Error("b200 loss: expects CUDA bf16 logits")
     if torch.is_tensor(num_items_in_batch):
         num_items_in_batch = float(num_items_in_batch)

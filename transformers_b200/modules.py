@@ -18,6 +18,13 @@ from . import functional as Fn
 from ._lib import B200Error
 
 ATTN_NAME = "b200"
+KERNEL_DTYPES = (torch.bfloat16,)
+
+
+def _on_b200(t: torch.Tensor) -> bool:
+    """Whether ``t`` takes the kernel path.  Off-GPU tensors defer to the stock reference forward (plumbing / CPU tests);
+    the kernels themselves never fall back (ops.py raises)."""
+    return t.is_cuda
 
 
 # ----------------------------------------------------------------------------------------------------- weight fusion
@@ -70,7 +77,7 @@ class B200RMSNormMixin:
     _b200_gemma = False
 
     def forward(self, hidden_states):  # LlamaRMSNorm.forward models/llama/modeling_llama.py:62-67
-        if not hidden_states.is_cuda:
+        if not _on_b200(hidden_states):
             return super().forward(hidden_states)
         eps = getattr(self, "variance_epsilon", None)
         if eps is None:
@@ -80,7 +87,7 @@ class B200RMSNormMixin:
 
 class B200MLPMixin:
     def forward(self, x):  # LlamaMLP.forward models/llama/modeling_llama.py:174-176
-        if not x.is_cuda:
+        if not _on_b200(x):
             return _tp_allreduce(self, super().forward(_tp_copy(self, x)))
         group = self.__dict__.get("_b200_tp_group")
         col = (group, "col") if group is not None else None
@@ -104,7 +111,7 @@ class B200AttentionMixin:
         return getattr(self.config, "sliding_window", None)  # Mistral (modeling_mistral.py:172); Llama: None
 
     def forward(self, hidden_states, position_embeddings=None, attention_mask=None, past_key_values=None, **kwargs):
-        if self.config._attn_implementation != ATTN_NAME or not hidden_states.is_cuda:
+        if self.config._attn_implementation != ATTN_NAME or not _on_b200(hidden_states):
             out, w = super().forward(_tp_copy(self, hidden_states), position_embeddings=position_embeddings,
                                      attention_mask=attention_mask, past_key_values=past_key_values, **kwargs)
             return _tp_allreduce(self, out), w
@@ -145,7 +152,7 @@ class B200AttentionMixin:
 class B200EmbeddingMixin:
     def forward(self, input_ids):  # nn.Embedding.forward; Gemma2TextScaledWordEmbedding models/gemma2/modeling_gemma2.py:348
         w = _local(self.weight)
-        if not w.is_cuda:
+        if not _on_b200(w):
             return super().forward(input_ids)
         scale = None
         if hasattr(self, "embed_scale"):
@@ -159,7 +166,7 @@ class B200LinearMixin:
     def forward(self, x):
         w = _local(self.weight)
         gather = self.__dict__.get("_b200_tp_gather", False)
-        if not w.is_cuda or self.bias is not None:
+        if not _on_b200(w) or self.bias is not None:
             y = super().forward(_tp_copy(self, x) if gather else x)
         else:
             col = (self.__dict__["_b200_tp_group"], "col") if gather else None
