@@ -25,7 +25,8 @@ ref = model(input_ids=ids, labels=ids); ref.loss.backward()
 ref_logits, ref_loss = ref.logits.detach().float().clone(), ref.loss.item()
 ref_g = {n: p.grad.detach().float().clone() for n, p in model.named_parameters()}
 model.zero_grad(set_to_none=True)
-tensor_parallelize(model)
+SP = int(os.environ.get("B200_TP_SP", "0"))  # >0: sequence parallel with that many pipelined chunks
+tensor_parallelize(model, sequence_parallel=SP > 0, chunks=max(SP, 1))
 out = model(input_ids=ids, labels=ids); out.loss.backward()
 err = (out.logits.float() - ref_logits).abs().max().item()
 styles = {"q_proj": 0, "k_proj": 0, "v_proj": 0, "gate_proj": 0, "up_proj": 0, "lm_head": 0, "o_proj": 1, "down_proj": 1}
@@ -35,6 +36,6 @@ for n, p in model.named_parameters():
     if leaf in styles: g = g.chunk(world, dim=styles[leaf])[rank]
     worst = max(worst, ((p.grad.float() - g).abs().max() / (g.abs().max() + 1e-8)).item())
 ok = err < 5e-2 and abs(out.loss.item() - ref_loss) < 2e-2 and worst < 5e-2
-print(f"rank {rank}/{world}: logits max err {err:.4f}, loss {out.loss.item():.4f} vs {ref_loss:.4f}, worst grad rel err {worst:.4f} -> {'OK' if ok else 'FAIL'}", flush=True)
+print(f"rank {rank}/{world} sp={SP}: logits max err {err:.4f}, loss {out.loss.item():.4f} vs {ref_loss:.4f}, worst grad rel err {worst:.4f} -> {'OK' if ok else 'FAIL'}", flush=True)
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

@@ -1,7 +1,12 @@
 """N>1 host logic on CPU: 2 processes over gloo.  Mirrors tests/test_tensor_parallel_mixin.py:199-287 of the reference
 (TP model vs single-process model: logits, loss, per-shard gradients; fp32, atol=rtol=1e-5).
-The compute on CPU tensors is the stock reference forward (our modules defer to it off-GPU); what is under test is OUR
-sharding by the reference's tp_plan and OUR collectives (copy_to_group / all_reduce_sum / gather_last_dim)."""
+
+Two compute modes, each with and without sequence parallelism:
+  "stock": CPU tensors take the stock reference forward (our modules defer to it off-GPU); under test is OUR sharding by
+           the reference's tp_plan and OUR collectives (copy_to_group / all_reduce_sum / gather_last_dim, and the
+           all-gather / reduce-scatter token sharding of parallel.SequenceParallelState);
+  "kernel-path": the fused autograd Functions of functional.py run (C-ABI calls replaced by tests/_fake_ops.py), i.e. the
+           chunked, overlapped collectives the GPU path issues around its GEMMs."""
 import os
 import socket
 import sys
@@ -21,7 +26,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, mode, sp, S=12):
     try:
         sys.path.insert(0, ROOT)
         sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -36,7 +41,7 @@ def _worker(rank, world, port, q):
 
         transformers_b200.enable()
         cfg = tf.LlamaConfig(vocab_size=160, hidden_size=64, intermediate_size=176, num_hidden_layers=2, num_attention_heads=4,
-                             num_key_value_heads=2, head_dim=16, max_position_embeddings=64,
+                             num_key_value_heads=2, head_dim=16, max_position_embeddings=512,
                              rope_parameters={"rope_type": "default", "rope_theta": 10000.0})
         tf.set_seed(0)
         model = tf.LlamaForCausalLM._from_config(cfg, attn_implementation="eager", dtype=torch.float32)
@@ -44,7 +49,8 @@ def _worker(rank, world, port, q):
         model.loss_function = None
         del model._loss_function
         torch.manual_seed(1)
-        ids = torch.randint(0, 160, (2, 12))
+        ids = torch.randint(0, 160, (2, S))
+        model.config.use_cache = False
         ref = model(input_ids=ids, labels=ids)
         ref.loss.backward()
         ref_grads = {n: p.grad.clone() for n, p in model.named_parameters()}
@@ -54,7 +60,12 @@ def _worker(rank, world, port, q):
         plan = resolve_plan(model)
         assert plan["model.layers.*.self_attn.q_proj"] == "colwise" and plan["model.layers.*.mlp.down_proj"] == "rowwise"
         assert plan["lm_head"] == "colwise_gather_output"
-        tensor_parallelize(model)
+        tensor_parallelize(model, sequence_parallel=sp, chunks=3)
+        if mode == "kernel-path":
+            import _fake_ops
+
+            _fake_ops.install()
+            model.set_attn_implementation("b200")
         att = model.model.layers[0].self_attn
         assert att.q_proj.weight.shape == (4 * 16 // world, 64) and att.k_proj.weight.shape == (2 * 16 // world, 64)
         assert att.o_proj.weight.shape == (64, 4 * 16 // world)
@@ -62,6 +73,17 @@ def _worker(rank, world, port, q):
         assert model.lm_head.weight.shape == (160 // world, 64)
         out = model(input_ids=ids, labels=ids)
         out.loss.backward()
+        if sp:
+            st = model._b200_sp
+            assert st.active and st.full_shape == (2, S, 64) and st.chunks == 3
+        if mode == "kernel-path":
+            names = [c[0] for c in _fake_ops.CALLS]
+            assert names.count("attn_fwd") == 2 and names.count("attn_bwd") == 2
+            shapes = [c[1][0] for c in _fake_ops.CALLS if c[0] == "gemm"]
+            if not sp and 2 * S >= 512:  # rowwise GEMMs (o, down) are issued in two row halves so the all-reduces overlap
+                assert sum(1 for sh in shapes if sh[0] == S) >= 2 * 2 * 2, shapes
+            if sp:  # every fused linear inside a block runs chunk by chunk: (qkv, o, gate|up, down) x (fwd, dgrad) x 3 chunks
+                assert sum(1 for sh in shapes if sh[0] == 24 // 3) == 2 * 4 * 2 * 3, shapes
         torch.testing.assert_close(out.logits, ref_logits, atol=1e-5, rtol=1e-5)
         torch.testing.assert_close(out.loss, ref_loss, atol=1e-5, rtol=1e-5)
         styles = {"q_proj": 0, "k_proj": 0, "v_proj": 0, "gate_proj": 0, "up_proj": 0, "lm_head": 0, "o_proj": 1, "down_proj": 1}
@@ -70,7 +92,7 @@ def _worker(rank, world, port, q):
             leaf = n.split(".")[-2]
             if leaf in styles:
                 g = g.chunk(world, dim=styles[leaf])[rank]
-            torch.testing.assert_close(p.grad, g, atol=1e-5, rtol=1e-4, msg=lambda m, n=n: f"{n}: {m}")
+            torch.testing.assert_close(p.grad, g, atol=1e-5 if S < 64 else 1e-4, rtol=1e-4, msg=lambda m, n=n: f"{n}: {m}")
         q.put((rank, "ok"))
     except Exception:
         q.put((rank, traceback.format_exc()))
@@ -80,12 +102,14 @@ def _worker(rank, world, port, q):
 
 
 @pytest.mark.timeout(300)
-def test_tp2_matches_single_process_gloo():
+@pytest.mark.parametrize("mode,sp,S", [("stock", False, 12), ("stock", True, 12), ("kernel-path", False, 12),
+                                       ("kernel-path", True, 12), ("kernel-path", False, 256)])
+def test_tp2_matches_single_process_gloo(mode, sp, S):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, mode, sp, S)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=280) for _ in range(world)]

@@ -23,6 +23,73 @@ def _tp_reduce_async(t, group):
     return dist.all_reduce(t, group=group, async_op=True)
 
 
+def _tp_unpack(tp):
+    """tp descriptor -> (group, mode, sequence-parallel state).  Modes: "col" / "row" (replicated activations, all-reduce)
+    and "col_sp" / "row_sp" (token-sharded activations between the blocks, parallel.SequenceParallelState)."""
+    if tp is None:
+        return None, None, None
+    return tp[0], tp[1], (tp[2] if len(tp) > 2 else None)
+
+
+def _sp_gather_gemm(x_local2, w, st):
+    """Colwise block entry under sequence parallelism: y = all_gather(x) @ w^T with the all-gather of chunk c+1 running
+    on the communicator's stream while chunk c is in the GEMM.  Returns (x_full [T,K] -- kept for the wgrad --, y [T,N])."""
+    from .parallel import sp_all_gather
+
+    x_full, works = sp_all_gather(x_local2, st)
+    y = x_full.new_empty(x_full.shape[0], w.shape[0])
+    for rows, work in zip(st.chunk_rows(x_full.shape[0]), works):
+        work.wait()
+        ops.gemm(x_full[rows], w, out=y[rows])
+    return x_full, y
+
+
+def _sp_dgrad_scatter(dy2, w, st):
+    """Colwise block entry, backward: dX = dY @ W is a partial sum over the ranks' column shards -> reduce-scatter it to
+    the token shards, chunk c's reduce-scatter running under chunk c+1's GEMM (and under the caller's wgrad GEMM).
+    Returns (dx_local [T/N,K], pending works, buffers to keep alive until the works are waited on)."""
+    from .parallel import sp_reduce_scatter_chunk
+
+    T = dy2.shape[0]
+    dx_local = dy2.new_empty(T // st.world, w.shape[1])
+    works, keep = [], []
+    for c, rows in enumerate(st.chunk_rows(T)):
+        part = ops.gemm(dy2[rows], w, b_mn=True)
+        keep.append(part)
+        works.append(sp_reduce_scatter_chunk(part, dx_local, c, st))
+    return dx_local, works, keep
+
+
+def _sp_gemm_scatter(x2, w, st):
+    """Rowwise block exit under sequence parallelism: reduce_scatter(x @ w^T), chunk c's reduce-scatter under chunk c+1's
+    GEMM.  Returns y_local [T/N, N]."""
+    from .parallel import sp_reduce_scatter_chunk
+
+    T = x2.shape[0]
+    y_local = x2.new_empty(T // st.world, w.shape[0])
+    works, keep = [], []
+    for c, rows in enumerate(st.chunk_rows(T)):
+        part = ops.gemm(x2[rows], w)
+        keep.append(part)
+        works.append(sp_reduce_scatter_chunk(part, y_local, c, st))
+    for work in works:
+        work.wait()
+    return y_local
+
+
+def _sp_gather_dgrad(dy_local2, w, st):
+    """Rowwise block exit, backward: dY arrives token-sharded -> all-gather it (chunk c+1 under chunk c's dgrad GEMM).
+    Returns (dy_full [T,N] -- for the wgrad --, dx [T,K])."""
+    from .parallel import sp_all_gather
+
+    dy_full, works = sp_all_gather(dy_local2, st)
+    dx = dy_full.new_empty(dy_full.shape[0], w.shape[1])
+    for rows, work in zip(st.chunk_rows(dy_full.shape[0]), works):
+        work.wait()
+        ops.gemm(dy_full[rows], w, b_mn=True, out=dx[rows])
+    return dy_full, dx
+
+
 class FusedLinearFn(torch.autograd.Function):
     """y = x @ cat(weights)^T  -- one GEMM for several nn.Linear layers that share their input
     (q/k/v: models/llama/modeling_llama.py:254-256; gate/up: :174-176) or a single one (o_proj, down_proj, lm_head).
@@ -43,9 +110,19 @@ class FusedLinearFn(torch.autograd.Function):
         if not x2.is_contiguous():
             x2 = x2.contiguous()
         N = w_fused.shape[0]
+        group, mode, st = _tp_unpack(tp)
+        ctx.splits = [w.shape[0] for w in weights]
+        ctx.x_shape = x.shape
+        ctx.tp = tp
+        if mode == "col_sp":  # x is this rank's token shard [1, T/N, K] -> y [1, T, N]
+            x_full, y2 = _sp_gather_gemm(x2, w_fused, st)
+            ctx.save_for_backward(x_full, w_fused)
+            return y2.view(1, -1, N)
+        if mode == "row_sp":  # x holds all tokens [.., K/N] -> y is this rank's token shard [1, T/N, N]
+            ctx.save_for_backward(x2, w_fused)
+            return _sp_gemm_scatter(x2, w_fused, st).view(1, -1, N)
         y = torch.empty(*x.shape[:-1], N, device=x.device, dtype=x.dtype)
         y2 = y.view(-1, N)
-        group, mode = tp if tp is not None else (None, None)
         T = x2.shape[0]
         if group is not None and mode == "row" and T >= 512:
             h = (T // 2 + 127) // 128 * 128
@@ -60,9 +137,6 @@ class FusedLinearFn(torch.autograd.Function):
             if group is not None and mode == "row":
                 _tp_reduce_async(y2, group).wait()
         ctx.save_for_backward(x2, w_fused)
-        ctx.splits = [w.shape[0] for w in weights]
-        ctx.x_shape = x.shape
-        ctx.tp = tp
         return y
 
     @staticmethod
@@ -72,9 +146,16 @@ class FusedLinearFn(torch.autograd.Function):
         dy2 = dy.reshape(-1, N)
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
-        group, mode = ctx.tp if ctx.tp is not None else (None, None)
-        dx, work = None, None
-        if _needs(ctx, 0):
+        group, mode, st = _tp_unpack(ctx.tp)
+        dx, work, works, keep = None, None, (), None
+        if mode == "row_sp":
+            dy2, dx = _sp_gather_dgrad(dy2, w_fused, st)  # dy2 is now the gathered [T, N]
+            dx = dx.view(ctx.x_shape)
+        elif mode == "col_sp":
+            if _needs(ctx, 0):
+                dx, works, keep = _sp_dgrad_scatter(dy2, w_fused, st)  # overlaps the wgrad GEMM below
+                dx = dx.view(ctx.x_shape)
+        elif _needs(ctx, 0):
             dx = ops.gemm(dy2, w_fused, b_mn=True).view(ctx.x_shape)  # dX = dY W : B stored [K'=N, N'=K]
             if mode == "col":
                 work = _tp_reduce_async(dx, group)  # overlaps the wgrad GEMM below
@@ -88,6 +169,9 @@ class FusedLinearFn(torch.autograd.Function):
                 off += n
         if work is not None:
             work.wait()
+        for w_ in works:
+            w_.wait()
+        del keep
         return (dx, None, None, *grads_w)
 
 
@@ -133,11 +217,18 @@ class QKVRopeAttentionFn(torch.autograd.Function):
     def forward(ctx, x, w_fused, cos, sin, cfg, kv_start, kv_end, tp, *weights):
         Hq, Hkv, D, scale, causal, window, softcap = cfg
         ctx.tp = tp
-        B, S, K = x.shape
-        x2 = x.reshape(B * S, K)
+        _, mode, st = _tp_unpack(tp)
+        K = x.shape[-1]
+        x2 = x.reshape(-1, K)
         if not x2.is_contiguous():
             x2 = x2.contiguous()
-        qkv = ops.gemm(x2, w_fused).view(B, S, -1)
+        if mode == "col_sp":  # x is this rank's token shard; (B, S) are those of the whole batch
+            B, S = st.full_shape[:2]
+            x2, qkv = _sp_gather_gemm(x2, w_fused, st)
+            qkv = qkv.view(B, S, -1)
+        else:
+            B, S = x.shape[:2]
+            qkv = ops.gemm(x2, w_fused).view(B, S, -1)
         ops.rope_(qkv, cos, sin, Hq + Hkv, D)
         q = qkv[..., : Hq * D].view(B, S, Hq, D)
         k = qkv[..., Hq * D:(Hq + Hkv) * D].view(B, S, Hkv, D)
@@ -169,8 +260,15 @@ class QKVRopeAttentionFn(torch.autograd.Function):
                      kv_start=kv_start, kv_end=kv_end)
         ops.rope_(dqkv, cos, sin, Hq + Hkv, D, backward=True)
         d2 = dqkv.view(B * S, W)
-        dx = ops.gemm(d2, w_fused, b_mn=True).view(ctx.x_shape) if _needs(ctx, 0) else None
-        work = _tp_reduce_async(dx, ctx.tp[0]) if (dx is not None and ctx.tp is not None) else None  # overlaps the wgrad
+        _, mode, st = _tp_unpack(ctx.tp)
+        dx, work, works, keep = None, None, (), None
+        if mode == "col_sp":
+            if _needs(ctx, 0):
+                dx, works, keep = _sp_dgrad_scatter(d2, w_fused, st)  # reduce-scatters overlap the wgrad
+                dx = dx.view(ctx.x_shape)
+        elif _needs(ctx, 0):
+            dx = ops.gemm(d2, w_fused, b_mn=True).view(ctx.x_shape)
+            work = _tp_reduce_async(dx, ctx.tp[0]) if ctx.tp is not None else None  # overlaps the wgrad
         grads_w = [None] * len(ctx.splits)
         if any(ctx.needs_input_grad[8:]):
             dw = ops.gemm(d2, x2, a_mn=True, b_mn=True)
@@ -181,6 +279,9 @@ class QKVRopeAttentionFn(torch.autograd.Function):
                 off += n
         if work is not None:
             work.wait()
+        for w_ in works:
+            w_.wait()
+        del keep
         return (dx, None, None, None, None, None, None, None, *grads_w)
 
 

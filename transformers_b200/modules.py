@@ -89,9 +89,7 @@ class B200MLPMixin:
     def forward(self, x):  # LlamaMLP.forward models/llama/modeling_llama.py:174-176
         if not _on_b200(x):
             return _tp_allreduce(self, super().forward(_tp_copy(self, x)))
-        group = self.__dict__.get("_b200_tp_group")
-        col = (group, "col") if group is not None else None
-        row = (group, "row") if group is not None else None
+        col, row, _ = _tp_modes(self)
         _check_no_bias(self.gate_proj, self.up_proj, self.down_proj)
         wg, wu, wd = _local(self.gate_proj.weight), _local(self.up_proj.weight), _local(self.down_proj.weight)
         act = getattr(self.config, "hidden_act", None) or getattr(self.config, "hidden_activation", "silu")
@@ -115,9 +113,7 @@ class B200AttentionMixin:
             out, w = super().forward(_tp_copy(self, hidden_states), position_embeddings=position_embeddings,
                                      attention_mask=attention_mask, past_key_values=past_key_values, **kwargs)
             return _tp_allreduce(self, out), w
-        group = self.__dict__.get("_b200_tp_group")
-        col = (group, "col") if group is not None else None
-        row = (group, "row") if group is not None else None
+        col, row, sp = _tp_modes(self)
         _check_no_bias(self.q_proj, self.k_proj, self.v_proj, self.o_proj)
         if self.training and getattr(self, "attention_dropout", 0.0):
             raise B200Error("transformers_b200: attention dropout is not supported")
@@ -125,7 +121,9 @@ class B200AttentionMixin:
                           _local(self.o_proj.weight))
         D = self.head_dim
         Hq, Hkv = wq.shape[0] // D, wk.shape[0] // D  # local head counts (module is head-count agnostic under TP)
-        B, S, _ = hidden_states.shape
+        # sequence parallel: hidden_states is this rank's token shard [1, T/N, H]; the all-gather happens inside the fused
+        # Function and (B, S) are those of the unsharded batch
+        B, S = sp.full_shape[:2] if sp is not None else hidden_states.shape[:2]
         cos, sin = position_embeddings
         window = self._b200_window() or 0
         softcap = getattr(self, "attn_logit_softcapping", None) or 0.0
@@ -178,22 +176,40 @@ class B200LinearMixin:
         return y
 
 
+def _sp_state(module):
+    st = module.__dict__.get("_b200_sp")
+    return st if st is not None and st.active else None
+
+
+def _tp_modes(module):
+    """(col, row, sp) descriptors for FusedLinearFn / QKVRopeAttentionFn: ``(group, mode[, sp_state])`` or None."""
+    group = module.__dict__.get("_b200_tp_group")
+    if group is None:
+        return None, None, None
+    sp = _sp_state(module)
+    if sp is not None:
+        return (group, "col_sp", sp), (group, "row_sp", sp), sp
+    return (group, "col"), (group, "row"), None
+
+
 def _tp_copy(module, x):
     group = module.__dict__.get("_b200_tp_group")
     if group is None:
         return x
-    from .parallel import copy_to_group
+    from . import parallel
 
-    return copy_to_group(x, group)
+    sp = _sp_state(module)
+    return parallel.gather_tokens(x, sp) if sp is not None else parallel.copy_to_group(x, group)
 
 
 def _tp_allreduce(module, out):
     group = module.__dict__.get("_b200_tp_group")
     if group is None:
         return out
-    from .parallel import all_reduce_sum
+    from . import parallel
 
-    return all_reduce_sum(out, group)
+    sp = _sp_state(module)
+    return parallel.reduce_scatter_tokens(out, sp) if sp is not None else parallel.all_reduce_sum(out, group)
 
 
 # --------------------------------------------------------------------------------------------------- class factories
