@@ -64,6 +64,9 @@ def parse():
     ap.add_argument("--sequence-parallel", type=int, default=int(os.environ.get("B200_TP_SP", "0")),
                     help="tp only: token-shard the residual stream between the blocks (all-gather / reduce-scatter instead of "
                          "all-reduce), N = chunks the collectives are pipelined in; 0 = plain tp_plan all-reduce")
+    ap.add_argument("--vocab-parallel-loss", type=int, default=int(os.environ.get("B200_TP_VOCAB_LOSS", "0")),
+                    help="tp only: keep lm_head's output vocabulary-sharded and exchange per-row loss statistics instead of "
+                         "all-gathering the logits")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -266,7 +269,7 @@ def run_b200(args):
         from transformers_b200.parallel import tensor_parallelize
 
         tensor_parallelize(model, dist.group.WORLD, sequence_parallel=args.sequence_parallel > 0,
-                           chunks=max(args.sequence_parallel, 1))
+                           chunks=max(args.sequence_parallel, 1), vocab_parallel_loss=bool(args.vocab_parallel_loss))
 
     B, S = args.batch, args.seq
     torch.manual_seed(0)
@@ -352,7 +355,8 @@ def run_b200(args):
             "config": {"workload": workload_name(world, B, S) if args.layers == 32
                        else f"DEBUG {args.layers}-layer model -- not the named config", "model": "Llama-3-8B (random init)",
                        "global_batch": B * replicas, "seq_len": S, "parallelism": (f"{parallelism}{world}" + (f"+sp{args.sequence_parallel}" if parallelism == "tp" and args.sequence_parallel > 0
-                                                                 else "")) if world > 1 else "single",
+                                                                 else "")
+                                       + ("+vocab-parallel-loss" if parallelism == "tp" and args.vocab_parallel_loss else "")) if world > 1 else "single",
                        "l2": "working set (16 GB weights + activations) >> 126 MB L2; no explicit flush needed",
                        "lm_head_and_loss": "included (b200 GEMM + fused CE kernels)"},
             "loss": float(loss.detach()), "model_tflops_per_gpu": per_gpu_tf,

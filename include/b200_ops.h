@@ -102,6 +102,12 @@ int b200_ce_fwd(const void* logits, const int64_t* labels, float* lse, float* lo
 int b200_ce_bwd(const void* logits, const int64_t* labels, const float* lse, const float* dloss, const float* denom,
                 void* dlogits, int B, int S, int V, int ld, int ld_out, int shift, int64_t ignore_index,
                 b200_stream_t stream);
+/* Same gradient for a vocabulary-sharded lm_head (tp_plan "colwise" on lm_head, models/llama/modeling_llama.py:423, without
+ * the gather of "colwise_gather_output"): logits holds this rank's V columns; lse_global is the log-sum-exp over the whole
+ * vocabulary (combined across ranks by the caller), target_local the target's column in this shard or a value outside
+ * [0, V), row_scale = dloss / denom for valid rows and 0 for ignored ones. */
+int b200_ce_bwd_sharded(const void* logits, const int64_t* target_local, const float* lse_global,
+                        const float* row_scale, void* dlogits, int T, int V, int ld, int ld_out, b200_stream_t stream);
 
 #ifdef __cplusplus
 }

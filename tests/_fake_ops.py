@@ -207,8 +207,22 @@ def ce_bwd(logits, labels, lse, dloss, denom, shift=True, ignore_index=-100):
     return p.to(logits.dtype).view(B, S, V)
 
 
+def ce_row_lse(logits):
+    _log("ce_row_lse", logits)
+    return torch.logsumexp(logits.float(), -1)
+
+
+def ce_bwd_sharded(logits, target_local, lse_global, row_scale):
+    T, V = logits.shape
+    p = torch.exp(logits.float() - lse_global[:, None])
+    mine = (target_local >= 0) & (target_local < V)
+    p[torch.arange(T)[mine], target_local[mine]] -= 1.0
+    _log("ce_bwd_sharded", logits)
+    return (p * row_scale[:, None]).to(logits.dtype)
+
+
 _NAMES = ["gemm", "embedding_fwd", "embedding_bwd", "rmsnorm_fwd", "rmsnorm_bwd", "rope_", "glu_fwd", "glu_bwd", "attn_fwd",
-          "attn_bwd", "ce_fwd", "ce_bwd"]
+          "attn_bwd", "ce_fwd", "ce_bwd", "ce_row_lse", "ce_bwd_sharded"]
 
 
 def install(setattr_fn=setattr):

@@ -26,7 +26,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, q, mode, sp, S=12):
+def _worker(rank, world, port, q, mode, sp, S=12, vp=False):
     try:
         sys.path.insert(0, ROOT)
         sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -60,12 +60,13 @@ def _worker(rank, world, port, q, mode, sp, S=12):
         plan = resolve_plan(model)
         assert plan["model.layers.*.self_attn.q_proj"] == "colwise" and plan["model.layers.*.mlp.down_proj"] == "rowwise"
         assert plan["lm_head"] == "colwise_gather_output"
-        tensor_parallelize(model, sequence_parallel=sp, chunks=3)
+        tensor_parallelize(model, sequence_parallel=sp, chunks=3, vocab_parallel_loss=vp)
         if mode == "kernel-path":
             import _fake_ops
 
             _fake_ops.install()
             model.set_attn_implementation("b200")
+            model.loss_function = transformers_b200.integration.b200_causal_lm_loss
         att = model.model.layers[0].self_attn
         assert att.q_proj.weight.shape == (4 * 16 // world, 64) and att.k_proj.weight.shape == (2 * 16 // world, 64)
         assert att.o_proj.weight.shape == (64, 4 * 16 // world)
@@ -84,6 +85,11 @@ def _worker(rank, world, port, q, mode, sp, S=12):
                 assert sum(1 for sh in shapes if sh[0] == S) >= 2 * 2 * 2, shapes
             if sp:  # every fused linear inside a block runs chunk by chunk: (qkv, o, gate|up, down) x (fwd, dgrad) x 3 chunks
                 assert sum(1 for sh in shapes if sh[0] == 24 // 3) == 2 * 4 * 2 * 3, shapes
+        if vp:  # labels were passed: lm_head kept its vocabulary shard and the loss exchanged per-row statistics only
+            assert out.logits.shape[-1] == 160 // world and "ce_bwd_sharded" in names and "ce_fwd" not in names
+            ref_logits = ref_logits.chunk(world, dim=-1)[rank]
+            with torch.no_grad():  # without labels (generate) the logits are gathered as the tp_plan says
+                assert model(input_ids=ids).logits.shape[-1] == 160
         torch.testing.assert_close(out.logits, ref_logits, atol=1e-5, rtol=1e-5)
         torch.testing.assert_close(out.loss, ref_loss, atol=1e-5, rtol=1e-5)
         styles = {"q_proj": 0, "k_proj": 0, "v_proj": 0, "gate_proj": 0, "up_proj": 0, "lm_head": 0, "o_proj": 1, "down_proj": 1}
@@ -102,14 +108,15 @@ def _worker(rank, world, port, q, mode, sp, S=12):
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("mode,sp,S", [("stock", False, 12), ("stock", True, 12), ("kernel-path", False, 12),
-                                       ("kernel-path", True, 12), ("kernel-path", False, 256)])
-def test_tp2_matches_single_process_gloo(mode, sp, S):
+@pytest.mark.parametrize("mode,sp,S,vp", [("stock", False, 12, False), ("stock", True, 12, False),
+                                          ("kernel-path", False, 12, False), ("kernel-path", True, 12, True),
+                                          ("kernel-path", False, 256, True)])
+def test_tp2_matches_single_process_gloo(mode, sp, S, vp):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q, mode, sp, S)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, mode, sp, S, vp)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=280) for _ in range(world)]

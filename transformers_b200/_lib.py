@@ -40,6 +40,7 @@ SIGNATURES = {
     "b200_attn_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i] + [_l] * 12 + [_f, _f, _i, _i, _p, _p, _p],
     "b200_attn_bwd": [_p] * 10 + [_i] * 7 + [_p, _f, _f, _i, _i, _p, _p, _p],
     "b200_ce_bwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _l, _p],
+    "b200_ce_bwd_sharded": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
 }
 _RESTYPES = {"b200_last_error": c_char_p}
 

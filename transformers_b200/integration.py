@@ -157,6 +157,9 @@ def b200_causal_lm_loss(logits, labels, vocab_size=None, num_items_in_batch=None
         raise B200Error("b200 loss: expects CUDA bf16 logits")
     if torch.is_tensor(num_items_in_batch):
         num_items_in_batch = float(num_items_in_batch)
+    shard_group = getattr(logits, "_b200_vocab_shard", None)
+    if shard_group is not None:  # lm_head left its output vocabulary-sharded (parallel.tensor_parallelize(vocab_parallel_loss=True))
+        return Fn.VocabParallelLossFn.apply(logits, labels, ignore_index, num_items_in_batch, shift, shard_group)
     if logits.dim() == 2:
         logits = logits.unsqueeze(0)
         labels = labels.reshape(1, -1)

@@ -169,6 +169,9 @@ class B200LinearMixin:
         else:
             col = (self.__dict__["_b200_tp_group"], "col") if gather else None
             y = Fn.FusedLinearFn.apply(x, fused_weight(self, "w", [w]), col, w)
+        if gather and self.__dict__.get("_b200_keep_vocab_shard", False):
+            y._b200_vocab_shard = self.__dict__["_b200_tp_group"]  # consumed by integration.b200_causal_lm_loss
+            return y
         if gather:
             from .parallel import gather_last_dim
 

@@ -349,3 +349,36 @@ def ce_bwd(logits: torch.Tensor, labels: torch.Tensor, lse: torch.Tensor, dloss:
     check(lib.b200_ce_bwd(lg.data_ptr(), labels.data_ptr(), lse.data_ptr(), dloss.data_ptr(), denom.data_ptr(), dl.data_ptr(), B, S,
                           V, lg.stride(0), V, int(shift), int(ignore_index), _stream()), "b200_ce_bwd")
     return dl.view(B, S, V)
+
+
+def ce_row_lse(logits: torch.Tensor) -> torch.Tensor:
+    """logits [T, V] bf16 -> fp32 log-sum-exp of every row over these V columns (b200_ce_fwd with no targets)."""
+    lib = _lib_ready()
+    _chk_bf16(logits)
+    T, V = logits.shape
+    lg = logits if logits.is_contiguous() else logits.contiguous()
+    dev = logits.device
+    labels = torch.full((T,), -100, device=dev, dtype=torch.int64)
+    lse = torch.empty(T, device=dev, dtype=torch.float32)
+    rows = torch.empty(T, device=dev, dtype=torch.float32)
+    scratch = torch.empty(2, device=dev, dtype=torch.float32)
+    check(lib.b200_ce_fwd(lg.data_ptr(), labels.data_ptr(), lse.data_ptr(), rows.data_ptr(), scratch.data_ptr(),
+                          scratch.data_ptr() + 4, 1, T, V, lg.stride(0), 0, -100, 1.0, _stream()), "b200_ce_fwd")
+    return lse
+
+
+def ce_bwd_sharded(logits: torch.Tensor, target_local: torch.Tensor, lse_global: torch.Tensor,
+                   row_scale: torch.Tensor) -> torch.Tensor:
+    """Vocabulary-sharded CE gradient: logits [T, V_local] bf16, target_local [T] int64 (outside [0, V_local) when another
+    rank owns the target), lse_global [T] fp32, row_scale [T] fp32 -> dlogits [T, V_local]."""
+    lib = _lib_ready()
+    _chk_bf16(logits)
+    T, V = logits.shape
+    lg = logits if logits.is_contiguous() else logits.contiguous()
+    dl = torch.empty(T, V, device=logits.device, dtype=BF16)
+    tl = target_local.contiguous().to(torch.int64)
+    ls = lse_global.contiguous().to(torch.float32)
+    rs = row_scale.contiguous().to(torch.float32)
+    check(lib.b200_ce_bwd_sharded(lg.data_ptr(), tl.data_ptr(), ls.data_ptr(), rs.data_ptr(), dl.data_ptr(), T, V, lg.stride(0),
+                                  V, _stream()), "b200_ce_bwd_sharded")
+    return dl

@@ -289,11 +289,33 @@ def resolve_plan(model) -> dict:
     return plan
 
 
+def _install_vocab_parallel_loss(model: nn.Module) -> None:
+    """When a forward carries ``labels`` and the loss is ours, lm_head skips the logits all-gather and the loss combines
+    per-row statistics across the ranks instead (functional.VocabParallelLossFn).  ``out.logits`` of such a forward is this
+    rank's vocabulary shard; forwards without labels (generate) still return gathered logits."""
+    from .integration import b200_causal_lm_loss
+
+    head = getattr(model, "lm_head", None)
+    if head is None or not head.__dict__.get("_b200_tp_gather", False):
+        raise ValueError("vocab_parallel_loss needs an lm_head sharded as colwise_gather_output")
+
+    def before(module, args, kwargs):
+        ours = getattr(module, "loss_function", None) is b200_causal_lm_loss
+        head.__dict__["_b200_keep_vocab_shard"] = bool(ours and kwargs.get("labels") is not None)
+
+    def after(module, args, kwargs, output):
+        head.__dict__["_b200_keep_vocab_shard"] = False
+
+    model.register_forward_pre_hook(before, with_kwargs=True)
+    model.register_forward_hook(after, with_kwargs=True, always_call=True)
+
+
 def tensor_parallelize(model: nn.Module, group=None, plan: dict | None = None, sequence_parallel: bool = False,
-                       chunks: int = 2) -> nn.Module:
+                       chunks: int = 2, vocab_parallel_loss: bool = False) -> nn.Module:
     """Shard an already materialised model in place (each rank keeps its slice) and tell the block modules which group
     to reduce over.  Mirrors apply_tensor_parallelism (distributed/tensor_parallel.py:773-796) for colwise / rowwise /
-    colwise_gather_output; embeddings and norms stay replicated.  ``sequence_parallel``: see the module docstring."""
+    colwise_gather_output; embeddings and norms stay replicated.  ``sequence_parallel``: see the module docstring;
+    ``vocab_parallel_loss``: see ``_install_vocab_parallel_loss``."""
     group = group if group is not None else dist.group.WORLD
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     plan = plan if plan is not None else resolve_plan(model)
@@ -336,4 +358,6 @@ def tensor_parallelize(model: nn.Module, group=None, plan: dict | None = None, s
                 mod.__dict__["_b200_sp"] = st
         _install_sequence_parallel(model, st, blocks)
         model.__dict__["_b200_sp"] = st
+    if vocab_parallel_loss and world > 1:
+        _install_vocab_parallel_loss(model)
     return model
