@@ -62,3 +62,24 @@ def test_c_abi_validates_arguments_without_a_gpu():
     assert lib.b200_attn_fwd(None, None, None, None, None, 128, 1, 8, 8, 4, 3, 128, *([8] * 12), 1.0, 0.0, 1, 0, None, None, None) == -22
     assert "multiple of Hkv" in _lib.last_error()
     assert lib.b200_moe_route(None, None, None, None, None, None, 4, 2, 0, None) == -22
+
+
+def test_bench_reference_arm_times_stock_layer_even_after_enable(monkeypatch):
+    """bench.py's CPU arm must run the reference library's own LlamaDecoderLayer (no B200 class in it), also in a process
+    where the plugin is enabled and a patched model has been built (the cpu_baseline leg of the b200 arm)."""
+    import bench
+    import transformers_b200
+
+    transformers = tf
+    transformers_b200.enable()
+    tiny = dict(bench.LLAMA3_8B, vocab_size=64, hidden_size=64, intermediate_size=128, num_attention_heads=4,
+                num_key_value_heads=2, head_dim=16, num_hidden_layers=2)
+    patched = transformers.LlamaForCausalLM._from_config(transformers.LlamaConfig(**tiny), attn_implementation="eager")
+    assert type(patched.model.layers[0].mlp).__name__ == "B200LlamaMLP"
+    monkeypatch.setattr(bench, "LLAMA3_8B", tiny)
+    got = bench.cpu_reference_sample_stock(seq=16, repeats=0)
+    assert got is not None and got[0] > 0 and got[2] == transformers.__version__
+    t, threads, kind, what = bench.cpu_sample(seq=16, repeats=0)
+    assert kind == "reference" and "stock transformers" in what
+    monkeypatch.setenv("B200_BENCH_ORACLE_BASELINE", "1")
+    assert bench.cpu_sample(seq=16, repeats=0)[2] == "port"
