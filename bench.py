@@ -67,6 +67,8 @@ def parse():
     ap.add_argument("--vocab-parallel-loss", type=int, default=int(os.environ.get("B200_TP_VOCAB_LOSS", "0")),
                     help="tp only: keep lm_head's output vocabulary-sharded and exchange per-row loss statistics instead of "
                          "all-gathering the logits")
+    ap.add_argument("--pack-weights", type=int, default=int(os.environ.get("B200_PACK_WEIGHTS", "0")),
+                    help="make q/k/v and gate/up weights row views of one buffer (no second fused copy in HBM)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -325,6 +327,9 @@ def run_b200(args):
 
         tensor_parallelize(model, dist.group.WORLD, sequence_parallel=args.sequence_parallel > 0,
                            chunks=max(args.sequence_parallel, 1), vocab_parallel_loss=bool(args.vocab_parallel_loss))
+
+    if args.pack_weights:
+        transformers_b200.pack_weights(model)
 
     B, S = args.batch, args.seq
     torch.manual_seed(0)

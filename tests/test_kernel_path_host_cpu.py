@@ -139,3 +139,37 @@ def test_gradient_checkpointing_replays_functions():
     ours.gradient_checkpointing_enable()
     torch.manual_seed(6)
     _compare(ref, ours, torch.randint(0, 160, (2, 16)))
+
+
+def test_packed_weights_are_parameter_views_and_survive_optimizer_steps():
+    from transformers_b200.modules import fused_weight
+
+    ref, ours = _pair(transformers.LlamaForCausalLM, _llama_cfg())
+    names_before = {k: v.shape for k, v in ours.state_dict().items()}
+    assert transformers_b200.pack_weights(ours) == 2 * 2  # (qkv, gate|up) x 2 layers
+    assert {k: v.shape for k, v in ours.state_dict().items()} == names_before
+    att = ours.model.layers[0].self_attn
+    ws = [att.q_proj.weight, att.k_proj.weight, att.v_proj.weight]
+    buf = fused_weight(att, "qkv", ws)
+    assert buf.data_ptr() == ws[0].data_ptr() and buf.shape[0] == sum(w.shape[0] for w in ws)
+    assert ws[1].data_ptr() == buf.data_ptr() + ws[0].numel() * 4  # adjacent row views, no copy
+    torch.manual_seed(7)
+    ids = torch.randint(0, 160, (2, 16))
+    _compare(ref, ours, ids)
+    # an optimizer step updates the parameters in place -> the packed operand follows without re-concatenation
+    opt_a = torch.optim.SGD(ref.parameters(), lr=0.1)
+    opt_b = torch.optim.SGD(ours.parameters(), lr=0.1)
+    opt_a.step()
+    opt_b.step()
+    assert fused_weight(att, "qkv", ws) is buf and torch.equal(buf[: ws[0].shape[0]], ws[0])
+    ref.zero_grad(set_to_none=True)
+    ours.zero_grad(set_to_none=True)
+    _compare(ref, ours, ids)
+    # re-allocating the parameters (dtype change) breaks the views: silently back to the cached concatenation
+    ours.to(torch.float64)
+    ws = [att.q_proj.weight, att.k_proj.weight, att.v_proj.weight]
+    again = fused_weight(att, "qkv", ws)
+    assert again.dtype == torch.float64 and torch.equal(again, torch.cat([w.detach() for w in ws]))
+    assert "qkv" not in att.__dict__["_b200_packed"]
+    transformers_b200.unpack_weights(ours)
+    assert "_b200_packed" not in att.__dict__

@@ -24,3 +24,15 @@ def accelerate(model, *args, **kwargs):
     from .integration import accelerate as _accelerate
 
     return _accelerate(model, *args, **kwargs)
+
+
+def pack_weights(model):
+    from .modules import pack_weights as _pack
+
+    return _pack(model)
+
+
+def unpack_weights(model):
+    from .modules import unpack_weights as _unpack
+
+    return _unpack(model)

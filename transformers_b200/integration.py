@@ -166,8 +166,9 @@ def b200_causal_lm_loss(logits, labels, vocab_size=None, num_items_in_batch=None
     return Fn.CausalLMLossFn.apply(logits, labels, ignore_index, num_items_in_batch, shift)
 
 
-def accelerate(model: nn.Module, attn: bool = True, head_and_loss: bool = True) -> nn.Module:
-    """Convert an already constructed reference model in place (class swap, parameters untouched)."""
+def accelerate(model: nn.Module, attn: bool = True, head_and_loss: bool = True, pack_weights: bool = False) -> nn.Module:
+    """Convert an already constructed reference model in place (class swap, parameters untouched).
+    ``pack_weights``: additionally make q/k/v and gate/up weights row views of one buffer (modules.pack_weights)."""
     enable()
     cmap = _class_map()
     by_base = {cls.__mro__[2]: cls for cls in cmap.values()}  # (B200X, mixin, base, ...)
@@ -192,4 +193,6 @@ def accelerate(model: nn.Module, attn: bool = True, head_and_loss: bool = True) 
                 c._experts_implementation = ATTN_NAME
             except Exception:
                 c._experts_implementation_internal = ATTN_NAME
+    if pack_weights:
+        M.pack_weights(model)
     return model

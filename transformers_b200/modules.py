@@ -34,6 +34,11 @@ def fused_weight(module: nn.Module, key: str, params: list[torch.Tensor]) -> tor
     if len(params) == 1:
         w = params[0]
         return w if w.is_contiguous() else w.contiguous()
+    packed = module.__dict__.get("_b200_packed")
+    if packed is not None and key in packed:
+        if _is_packed(packed[key], params):
+            return packed[key]  # the parameters ARE row views of this buffer: nothing to concatenate, ever
+        del packed[key]  # the parameters were re-allocated (.to(), load with assign=True, TP re-shard): fall back to the copy
     sig = tuple((p.data_ptr(), p._version, tuple(p.shape)) for p in params)
     cache = module.__dict__.setdefault("_b200_fused", {})
     hit = cache.get(key)
@@ -43,6 +48,64 @@ def fused_weight(module: nn.Module, key: str, params: list[torch.Tensor]) -> tor
         buf = torch.cat([p.detach() for p in params], dim=0).contiguous()
     cache[key] = (sig, buf)
     return buf
+
+
+def _is_packed(buf: torch.Tensor, params: list[torch.Tensor]) -> bool:
+    if buf.dim() != 2 or not buf.is_contiguous() or sum(p.shape[0] for p in params) != buf.shape[0]:
+        return False
+    K, ptr, es = buf.shape[1], buf.data_ptr(), buf.element_size()
+    for p in params:
+        if (p.dim() != 2 or p.shape[1] != K or p.dtype != buf.dtype or p.device != buf.device or p.stride() != (K, 1)
+                or p.data_ptr() != ptr):
+            return False
+        ptr += p.shape[0] * K * es
+    return True
+
+
+PACK_GROUPS = {"qkv": ("q_proj", "k_proj", "v_proj"), "gate_up": ("gate_proj", "up_proj")}
+
+
+def pack_weights(model: nn.Module) -> int:
+    """Checkpoint-compatible fused weight layout: re-home the q/k/v and the gate/up projection weights
+    of every block as adjacent row views of ONE contiguous buffer.  Names, shapes and ``state_dict`` are unchanged (each
+    ``*_proj.weight`` is still its own Parameter, optimizers update it in place), but the packed operand of the fused GEMM
+    now IS the parameter storage: no second copy in HBM (-9 GB for Llama-3-8B) and no re-concatenation after every
+    optimizer step.  Returns the number of groups packed.  Call after ``.cuda()`` / ``tensor_parallelize``; a later
+    re-allocation of the parameters silently falls back to the cached concatenation."""
+    n = 0
+    for mod in model.modules():
+        if not isinstance(mod, (B200AttentionMixin, B200MLPMixin)):
+            continue
+        for key, names in PACK_GROUPS.items():
+            lins = [getattr(mod, nm, None) for nm in names]
+            if any(not isinstance(lin, nn.Linear) or lin.bias is not None or hasattr(lin.weight, "to_local") for lin in lins):
+                continue
+            ws = [lin.weight for lin in lins]
+            if len({(w.dtype, w.device, w.shape[1]) for w in ws}) != 1:
+                continue
+            with torch.no_grad():
+                buf = torch.cat([w.detach() for w in ws], dim=0).contiguous()
+                off = 0
+                for w in ws:
+                    w.data = buf[off:off + w.shape[0]]
+                    off += w.shape[0]
+            mod.__dict__.setdefault("_b200_packed", {})[key] = buf
+            mod.__dict__.get("_b200_fused", {}).pop(key, None)
+            n += 1
+    return n
+
+
+def unpack_weights(model: nn.Module) -> None:
+    """Undo ``pack_weights`` (every parameter gets its own storage again), e.g. before a safetensors export that rejects
+    tensors sharing storage."""
+    for mod in model.modules():
+        packed = mod.__dict__.pop("_b200_packed", None)
+        if not packed:
+            continue
+        for key in packed:
+            for nm in PACK_GROUPS[key]:
+                w = getattr(mod, nm).weight
+                w.data = w.data.clone()
 
 
 def _local(p: torch.Tensor) -> torch.Tensor:
