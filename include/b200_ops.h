@@ -109,6 +109,26 @@ int b200_ce_bwd(const void* logits, const int64_t* labels, const float* lse, con
 int b200_ce_bwd_sharded(const void* logits, const int64_t* target_local, const float* lse_global,
                         const float* row_scale, void* dlogits, int T, int V, int ld, int ld_out, b200_stream_t stream);
 
+/* ---- optimizer step after the path ---------------------------------------------------------------
+ * Trainer clips the global gradient norm (trainer.py:1783-1785, _clip_grad_norm :2538-2542 -> torch.nn.utils.clip_grad_norm_)
+ * and calls optimizer.step() (:1788) on torch.optim.AdamW (trainer_optimizer.py:201-208).  Multi-tensor, one launch per
+ * param group.  tensor_table: device int64 [n_tensors][6] = {param*, grad*, exp_avg*, exp_avg_sq*, numel, 0} (bf16 params
+ * and grads; moments bf16 or fp32); chunk_map: device int32 [n_chunks][2] = {tensor index, chunk index} with chunks of
+ * b200_optim_chunk_elems() elements. */
+int b200_optim_chunk_elems(void);
+/* torch.optim.AdamW update with step_size = lr / bias_correction1, denom = sqrt(v) / bias_correction2_sqrt + eps; every
+ * gradient is multiplied by *grad_scale first when grad_scale != NULL (fused clipping: pass out2 + 1 of b200_grad_norm). */
+int b200_adamw_step(const int64_t* tensor_table, const int32_t* chunk_map, int n_chunks, int state_is_fp32, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, float bias_correction1,
+                    float bias_correction2_sqrt, const float* grad_scale, b200_stream_t stream);
+/* out2[0] = L2 norm over all gradients in the table (fp32 partial sums per chunk in partial_ws [n_chunks], combined in
+ * double: deterministic), out2[1] = clip coefficient min(1, max_norm / (norm + 1e-6)) (1 when max_norm <= 0). */
+int b200_grad_norm(const int64_t* tensor_table, const int32_t* chunk_map, int n_chunks, float* partial_ws, float max_norm,
+                   float* out2, b200_stream_t stream);
+/* grad *= *coef in place (no traffic when *coef == 1). */
+int b200_grad_scale(const int64_t* tensor_table, const int32_t* chunk_map, int n_chunks, const float* coef,
+                    b200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

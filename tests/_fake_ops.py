@@ -221,8 +221,61 @@ def ce_bwd_sharded(logits, target_local, lse_global, row_scale):
     return (p * row_scale[:, None]).to(logits.dtype)
 
 
+# ---- optimizer: the "device pointers" of the tables are resolved through a registry of live CPU tensors
+_PTRS = {}
+
+
+def register_tensors(*ts):
+    for t in ts:
+        _PTRS[t.data_ptr()] = t
+
+
+def optim_chunk_elems():
+    return 32768
+
+
+def _rows(table):
+    return [tuple(int(x) for x in r) for r in table.tolist()]
+
+
+def adamw_step(table, chunk_map, *, state_fp32, lr, beta1, beta2, eps, weight_decay, bias_correction1, bias_correction2_sqrt,
+               grad_scale=None):
+    chunk = optim_chunk_elems()
+    seen = {}
+    for ti, ci in chunk_map.tolist():
+        seen.setdefault(ti, []).append(ci)
+    gs = float(grad_scale[0]) if grad_scale is not None else 1.0
+    for ti, (pp, gp, mp, vp, n, _) in enumerate(_rows(table)):
+        assert seen.get(ti) == list(range((n + chunk - 1) // chunk)), "chunk map must cover every tensor exactly once"
+        p, g, m, v = _PTRS[pp], _PTRS[gp], _PTRS[mp], _PTRS[vp]
+        assert p.numel() == n and (m.dtype == torch.float32) == bool(state_fp32)
+        pf, gf, mf, vf = p.float(), g.float() * gs, m.float(), v.float()
+        pf = pf - lr * weight_decay * pf
+        mf = mf + (gf - mf) * (1.0 - beta1)
+        vf = beta2 * vf + (1.0 - beta2) * gf * gf
+        pf = pf - (lr / bias_correction1) * (mf / (vf.sqrt() / bias_correction2_sqrt + eps))
+        p.copy_(pf)
+        m.copy_(mf)
+        v.copy_(vf)
+    _log("adamw_step", table)
+
+
+def grad_norm(table, chunk_map, max_norm=0.0):
+    tot = sum(float((_PTRS[gp].double() ** 2).sum()) for _, gp, _, _, _, _ in _rows(table)) ** 0.5
+    coef = min(1.0, max_norm / (tot + 1e-6)) if max_norm > 0 else 1.0
+    _log("grad_norm", table)
+    return torch.tensor([tot, coef], dtype=torch.float32)
+
+
+def grad_scale_(table, chunk_map, coef):
+    for _, gp, _, _, _, _ in _rows(table):
+        _PTRS[gp].mul_(float(coef[0]))
+    _log("grad_scale_", table)
+
+
 _NAMES = ["gemm", "embedding_fwd", "embedding_bwd", "rmsnorm_fwd", "rmsnorm_bwd", "rope_", "glu_fwd", "glu_bwd", "attn_fwd",
-          "attn_bwd", "ce_fwd", "ce_bwd", "ce_row_lse", "ce_bwd_sharded"]
+          "attn_bwd", "ce_fwd", "ce_bwd", "ce_row_lse", "ce_bwd_sharded", "optim_chunk_elems",
+          "adamw_step", "grad_norm", "grad_scale_"]
 
 
 def install(setattr_fn=setattr):

@@ -5,6 +5,7 @@ huggingface/transformers' own extension points (AttentionInterface, AttentionMas
     transformers_b200.enable()                       # register "b200" + module patches
     model = AutoModelForCausalLM.from_config(cfg, attn_implementation="b200", dtype=torch.bfloat16).cuda()
     transformers_b200.accelerate(model)              # embedding gather, lm_head GEMM, fused causal-LM loss
+    from transformers_b200.optim import B200AdamW    # Trainer(optimizer_cls_and_kwargs=(B200AdamW, {...})): fused multi-tensor step
 
 Host code is Python/PyTorch (device memory, streams, torch.distributed); every hot op is a hand-written CUDA kernel
 reached through the C-ABI in ``include/b200_ops.h`` (``transformers_b200/lib/libb200.so``).  No CPU fallback exists.

@@ -41,6 +41,10 @@ SIGNATURES = {
     "b200_attn_bwd": [_p] * 10 + [_i] * 7 + [_p, _f, _f, _i, _i, _p, _p, _p],
     "b200_ce_bwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _l, _p],
     "b200_ce_bwd_sharded": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "b200_optim_chunk_elems": [],
+    "b200_adamw_step": [_p, _p, _i, _i, _f, _f, _f, _f, _f, _f, _f, _p, _p],
+    "b200_grad_norm": [_p, _p, _i, _p, _f, _p, _p],
+    "b200_grad_scale": [_p, _p, _i, _p, _p],
 }
 _RESTYPES = {"b200_last_error": c_char_p}
 

@@ -17,7 +17,7 @@ from ._lib import check as _check
 BF16 = torch.bfloat16
 
 # kernels launched per C-ABI entry point
-_KERNELS_PER_CALL = {"b200_rmsnorm_bwd": 2, "b200_ce_fwd": 2, "b200_attn_bwd": 3, "b200_moe_route": 3}
+_KERNELS_PER_CALL = {"b200_rmsnorm_bwd": 2, "b200_ce_fwd": 2, "b200_attn_bwd": 3, "b200_moe_route": 3, "b200_grad_norm": 2}
 
 
 def check(rc: int, what: str) -> None:
@@ -382,3 +382,36 @@ def ce_bwd_sharded(logits: torch.Tensor, target_local: torch.Tensor, lse_global:
     check(lib.b200_ce_bwd_sharded(lg.data_ptr(), tl.data_ptr(), ls.data_ptr(), rs.data_ptr(), dl.data_ptr(), T, V, lg.stride(0),
                                   V, _stream()), "b200_ce_bwd_sharded")
     return dl
+
+
+# ------------------------------------------------------------------------------------------------------ optimizer
+def optim_chunk_elems() -> int:
+    return int(_lib.load().b200_optim_chunk_elems())
+
+
+def adamw_step(table: torch.Tensor, chunk_map: torch.Tensor, *, state_fp32: bool, lr: float, beta1: float, beta2: float,
+               eps: float, weight_decay: float, bias_correction1: float, bias_correction2_sqrt: float,
+               grad_scale: torch.Tensor | None = None) -> None:
+    """One AdamW update of every tensor listed in ``table`` (device int64 [n,6], see include/b200_ops.h), in place."""
+    lib = _lib_ready()
+    check(lib.b200_adamw_step(table.data_ptr(), chunk_map.data_ptr(), chunk_map.shape[0], int(state_fp32), float(lr), float(beta1),
+                              float(beta2), float(eps), float(weight_decay), float(bias_correction1),
+                              float(bias_correction2_sqrt), grad_scale.data_ptr() if grad_scale is not None else None,
+                              _stream()), "b200_adamw_step")
+
+
+def grad_norm(table: torch.Tensor, chunk_map: torch.Tensor, max_norm: float = 0.0) -> torch.Tensor:
+    """-> fp32 [2] on the device: (global L2 norm of the listed gradients, clip coefficient for ``max_norm``)."""
+    lib = _lib_ready()
+    n = chunk_map.shape[0]
+    ws = torch.empty(max(n, 1), device=table.device, dtype=torch.float32)
+    out = torch.empty(2, device=table.device, dtype=torch.float32)
+    check(lib.b200_grad_norm(table.data_ptr(), chunk_map.data_ptr(), n, ws.data_ptr(), float(max_norm), out.data_ptr(), _stream()),
+          "b200_grad_norm")
+    return out
+
+
+def grad_scale_(table: torch.Tensor, chunk_map: torch.Tensor, coef: torch.Tensor) -> None:
+    lib = _lib_ready()
+    check(lib.b200_grad_scale(table.data_ptr(), chunk_map.data_ptr(), chunk_map.shape[0], coef.data_ptr(), _stream()),
+          "b200_grad_scale")
