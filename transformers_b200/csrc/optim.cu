@@ -23,15 +23,24 @@ constexpr int OPT_CHUNK = 32768;
 constexpr int OPT_THREADS = 256;
 
 struct AdamArgs {
-  float lr, beta1, beta2, eps, weight_decay, step_size, bc2_sqrt;
+  float lr, beta1, beta2, eps, weight_decay, step_size, inv_bc2_sqrt;
 };
+
+// approximate sqrt / division (<= 2 ulp in fp32): the stored results are rounded to bf16 (or feed a bf16 parameter), and
+// IEEE sqrt + two IEEE divisions per element would make this 14 B/element stream ALU-bound (measured on the GLU kernels,
+// profiles/README.md)
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __device__ __forceinline__ void adamw_update(float& p, float g, float& m, float& v, const AdamArgs& a) {
   p -= a.lr * a.weight_decay * p;                         // decoupled weight decay
   m = m + (g - m) * (1.f - a.beta1);                      // exp_avg.lerp_(grad, 1 - beta1)
   v = a.beta2 * v + (1.f - a.beta2) * g * g;              // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
-  const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;      // (sqrt(v) / sqrt(1 - beta2^t)) + eps
-  p -= a.step_size * (m / denom);                         // step_size = lr / (1 - beta1^t)
+  const float denom = sqrt_approx(v) * a.inv_bc2_sqrt + a.eps;  // (sqrt(v) / sqrt(1 - beta2^t)) + eps
+  p -= a.step_size * __fdividef(m, denom);                // step_size = lr / (1 - beta1^t)
 }
 
 __device__ __forceinline__ void load8(const __nv_bfloat16* ptr, float (&f)[8]) {
@@ -215,7 +224,7 @@ extern "C" int b200_adamw_step(const int64_t* tensor_table, const int32_t* chunk
   B200_REQUIRE(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f && lr >= 0.f && weight_decay >= 0.f,
                "adamw_step: hyper-parameters out of range");
   if (n_chunks == 0) return B200_OK;
-  AdamArgs a{lr, beta1, beta2, eps, weight_decay, lr / bias_correction1, bias_correction2_sqrt};
+  AdamArgs a{lr, beta1, beta2, eps, weight_decay, lr / bias_correction1, 1.f / bias_correction2_sqrt};
   const int2* chunks = reinterpret_cast<const int2*>(chunk_map);
   if (state_is_fp32)
     adamw_multi_kernel<float><<<n_chunks, OPT_THREADS, 0, stream>>>(tensor_table, chunks, a, grad_scale);
