@@ -1,0 +1,28 @@
+#!/usr/bin/env bash
+# First GPU call of the next round: validates everything that was written after round 1's GPU budget was spent
+# (never run on a device), cheapest first.  Usage (2 GPUs, ~6 min of box time):
+#   gpurun --gpus 2 --timeout 900 -- 'bash tests/cuda/round2_validate.sh 2>&1 | tee gpurun_out/round2_validate.log'
+# Every step is bounded by `timeout`; a failing step is reported and the script goes on.
+set -u
+cd "$(dirname "$0")/../.."
+mkdir -p gpurun_out
+N=${N:-2}
+run() { echo "=== $*"; timeout "${T:-300}" "$@"; echo "--- exit $?"; }
+
+# 1. single-GPU kernels: vocabulary-sharded CE backward, multi-tensor AdamW / grad-norm / scale
+T=300 run env B200_EXPERIMENTAL=1 python -m pytest tests/test_experimental_gpu.py -q -m gpu
+# 2. regular suite still green on this build
+T=600 run python -m pytest tests -x -q -m gpu
+# 3. NCCL parity of the tensor-parallel variants on a tiny model (logits / loss / gradient shards vs single GPU)
+for cfg in "0 0" "2 0" "0 1" "2 1" "4 1"; do
+  set -- $cfg
+  T=240 run env B200_TP_SP=$1 B200_TP_VOCAB_LOSS=$2 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" \
+    --master-addr 127.0.0.1 --master-port 29611 tests/cuda/tp_check.py
+done
+# 4. what the variants buy at the real shapes (8 of 32 layers: relative numbers only, NOT a bench value)
+for flags in "" "--sequence-parallel 2" "--sequence-parallel 4" "--sequence-parallel 2 --vocab-parallel-loss 1"; do
+  T=300 run python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port 29612 \
+    bench.py --gpus "$N" --steps 3 --warmup 3 --layers 8 --no-cpu-baseline $flags
+done
+# 5. packed weights (parameters as views of the fused buffer) on one GPU, 8 layers
+T=300 run python bench.py --steps 3 --warmup 3 --layers 8 --no-cpu-baseline --pack-weights 1
