@@ -13,6 +13,10 @@ run() { echo "=== $*"; timeout "${T:-300}" "$@"; echo "--- exit $?"; }
 T=300 run env B200_EXPERIMENTAL=1 python -m pytest tests/test_experimental_gpu.py -q -m gpu
 # 2. regular suite still green on this build
 T=600 run python -m pytest tests -x -q -m gpu
+# 2b. attention forward softmax variant (batched TMEM loads, split max / sum chains): parity, then timing next to the default
+T=600 run env B200_ATTN_FWD_ILP=1 python -m pytest tests/test_kernels_gpu.py tests/test_model_gpu.py -x -q -m gpu -k "attn or attention or llama"
+T=300 run python tests/cuda/bringup_attn.py
+T=300 run env B200_ATTN_FWD_ILP=1 python tests/cuda/bringup_attn.py
 # 3. NCCL parity of the tensor-parallel variants on a tiny model (logits / loss / gradient shards vs single GPU)
 for cfg in "0 0" "2 0" "0 1" "2 1" "4 1"; do
   set -- $cfg

@@ -17,6 +17,8 @@
 //   epilogue (warps 2-5):   O / l -> bf16 -> global [B, Sq, Hq, D]; LSE (natural log) for the backward pass.
 #include "attn_common.cuh"
 
+#include <stdlib.h>
+
 namespace b200 {
 
 constexpr int ATT_BM = 128;
@@ -60,7 +62,7 @@ __device__ __forceinline__ KvRange kv_range(const AttnFwdParams& p, int b, int q
   return r;
 }
 
-template <int D, bool SOFTCAP>
+template <int D, bool SOFTCAP, bool ILP>
 __global__ void __launch_bounds__(ATT_THREADS, D <= 128 ? 2 : 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, AttnFwdParams p) {
@@ -184,13 +186,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_wait(s_full, it & 1);
       tc_fence_after();
       float s[ATT_BN];
+      if constexpr (ILP) {
+        // all four 32-column loads in flight, one wait (the baseline pays the TMEM read latency four times in a row)
+        uint32_t r[ATT_BN / 32][32];
 #pragma unroll
-      for (int c = 0; c < ATT_BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tlane + S_COL + c * 32, r);
+        for (int c = 0; c < ATT_BN / 32; ++c) tmem_ld_32x32b_x32(tlane + S_COL + c * 32, r[c]);
         tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 32; ++e) s[c * 32 + e] = __uint_as_float(r[e]);
+        for (int c = 0; c < ATT_BN / 32; ++c) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) s[c * 32 + e] = __uint_as_float(r[c][e]);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < ATT_BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tlane + S_COL + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) s[c * 32 + e] = __uint_as_float(r[e]);
+        }
       }
       if (SOFTCAP) {
 #pragma unroll
@@ -211,9 +226,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (col >= hi || col < lo) s[e] = -INFINITY;
         }
       }
-      float m_tile = s[0];
+      float m_tile;
+      if constexpr (ILP) {
+        // four independent max chains of depth 32 instead of one of depth 128 (two softmax warps per scheduler cannot
+        // hide a 128-deep dependent chain)
+        float m4[4] = {s[0], s[1], s[2], s[3]};
 #pragma unroll
-      for (int e = 1; e < ATT_BN; ++e) m_tile = fmaxf(m_tile, s[e]);
+        for (int e = 4; e < ATT_BN; e += 4) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) m4[j] = fmaxf(m4[j], s[e + j]);
+        }
+        m_tile = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      } else {
+        m_tile = s[0];
+#pragma unroll
+        for (int e = 1; e < ATT_BN; ++e) m_tile = fmaxf(m_tile, s[e]);
+      }
       const float m_cand = fmaxf(m_ref, m_tile);
       const bool need = (m_cand - m_ref) * c2 > 8.0f;  // lazy rescale threshold (2^8 headroom in fp32 / bf16 P)
       float alpha = 1.0f;
@@ -241,17 +269,38 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       const float mc = (m_ref == -INFINITY) ? 0.f : m_ref * c2;
       float lsum = 0.f;
+      if constexpr (ILP) {
+        float la[ATT_BN / 32], lb[ATT_BN / 32];  // eight independent partial row sums (depth 16 each)
 #pragma unroll
-      for (int c = 0; c < ATT_BN / 32; ++c) {
-        uint32_t pk[16];
+        for (int c = 0; c < ATT_BN / 32; ++c) {
+          uint32_t pk[16];
+          la[c] = 0.f;
+          lb[c] = 0.f;
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const float p0 = fast_exp2(fmaf(s[c * 32 + 2 * e], c2, -mc));
-          const float p1 = fast_exp2(fmaf(s[c * 32 + 2 * e + 1], c2, -mc));
-          lsum += p0 + p1;
-          pk[e] = pack_bf16(p0, p1);
+          for (int e = 0; e < 16; ++e) {
+            const float p0 = fast_exp2(fmaf(s[c * 32 + 2 * e], c2, -mc));
+            const float p1 = fast_exp2(fmaf(s[c * 32 + 2 * e + 1], c2, -mc));
+            la[c] += p0;
+            lb[c] += p1;
+            pk[e] = pack_bf16(p0, p1);
+          }
+          tmem_st_32x32b_x16(tlane + P_COL + c * 16, pk);
         }
-        tmem_st_32x32b_x16(tlane + P_COL + c * 16, pk);
+#pragma unroll
+        for (int c = 0; c < ATT_BN / 32; ++c) lsum += la[c] + lb[c];
+      } else {
+#pragma unroll
+        for (int c = 0; c < ATT_BN / 32; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float p0 = fast_exp2(fmaf(s[c * 32 + 2 * e], c2, -mc));
+            const float p1 = fast_exp2(fmaf(s[c * 32 + 2 * e + 1], c2, -mc));
+            lsum += p0 + p1;
+            pk[e] = pack_bf16(p0, p1);
+          }
+          tmem_st_32x32b_x16(tlane + P_COL + c * 16, pk);
+        }
       }
       l += lsum;
       tmem_st_wait();
@@ -305,10 +354,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
-template <int D, bool SOFTCAP>
-static int launch_attn_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnFwdParams& p,
-                           cudaStream_t stream) {
-  auto kern = attn_fwd_kernel<D, SOFTCAP>;
+template <int D, bool SOFTCAP, bool ILP>
+static int launch_attn_fwd_v(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnFwdParams& p,
+                             cudaStream_t stream) {
+  auto kern = attn_fwd_kernel<D, SOFTCAP, ILP>;
   constexpr int smem = 3 * 128 * D * 2 + 128 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
@@ -320,6 +369,18 @@ static int launch_attn_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const C
   kern<<<grid, ATT_THREADS, smem, stream>>>(tq, tk, tv, p);
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
+}
+
+// B200_ATTN_FWD_ILP=1 selects the softmax variant with batched TMEM loads and split max / sum chains (written after the
+// round-1 GPU budget was spent: same math, different instruction schedule; to be measured before it becomes the default)
+template <int D, bool SOFTCAP>
+static int launch_attn_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnFwdParams& p,
+                           cudaStream_t stream) {
+  static const bool ilp = [] {
+    const char* e = getenv("B200_ATTN_FWD_ILP");
+    return e && atoi(e) > 0;
+  }();
+  return ilp ? launch_attn_fwd_v<D, SOFTCAP, true>(tq, tk, tv, p, stream) : launch_attn_fwd_v<D, SOFTCAP, false>(tq, tk, tv, p, stream);
 }
 
 }  // namespace b200
