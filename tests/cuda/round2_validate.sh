@@ -30,3 +30,9 @@ for flags in "" "--sequence-parallel 2" "--sequence-parallel 4" "--sequence-para
 done
 # 5. packed weights (parameters as views of the fused buffer) on one GPU, 8 layers
 T=300 run python bench.py --steps 3 --warmup 3 --layers 8 --no-cpu-baseline --pack-weights 1
+# 6. GEMM DRAM re-reads (profiles/README.md: 2-8x the algorithmic bytes): rasterisation group size sweep under ncu
+#    (one GPU; ncu numbers are for traffic only, never a bench value)
+for gm in 2 4 8 16 32; do
+  T=300 run env B200_GEMM2_GROUP_M=$gm ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
+    --clock-control none -k regex:gemm_bf16 --csv --log-file gpurun_out/gemm_traffic_gm$gm.csv python tests/cuda/prof_kernels.py gemm
+done
