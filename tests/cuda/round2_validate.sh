@@ -36,3 +36,9 @@ for gm in 2 4 8 16 32; do
   T=300 run env B200_GEMM2_GROUP_M=$gm ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
     --clock-control none -k regex:gemm_bf16 --csv --log-file gpurun_out/gemm_traffic_gm$gm.csv python tests/cuda/prof_kernels.py gemm
 done
+# 7. GEMM lock-step variant: parity (all GEMM tests with the sync forced on for every K), then traffic + time next to step 6's gm=8
+T=600 run env B200_GEMM2_SYNC=1 B200_GEMM2_SYNC_MIN_K=1 python -m pytest tests/test_kernels_gpu.py -x -q -m gpu -k gemm
+T=300 run env B200_GEMM2_SYNC=1 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
+  --clock-control none -k regex:gemm_bf16 --csv --log-file gpurun_out/gemm_traffic_sync.csv python tests/cuda/prof_kernels.py gemm
+T=300 run env B200_GEMM2_SYNC=1 python bench.py --steps 3 --warmup 3 --layers 8 --no-cpu-baseline
+T=300 run python bench.py --steps 3 --warmup 3 --layers 8 --no-cpu-baseline

@@ -30,9 +30,31 @@ struct Gemm2Params {
   int accumulate;
   int group_m;
   uint32_t a_lbo, a_sbo, b_lbo, b_sbo;
+  // SYNC variant only: soft lock-step of the clusters at tile boundaries (see soft_grid_sync)
+  unsigned long long* sync_ctr;
+  unsigned long long sync_base;
+  int sync_rounds;
 };
 
-template <int A_MN, int B_MN>
+// Co-running tiles share A row panels / B column panels through L2 only while they walk K together.  Nothing keeps the
+// 74 persistent clusters in step: after a few tiles their start times have drifted by more than L2 can bridge and the
+// same k-blocks are fetched from DRAM again (ncu: 4.9-10.6 GB per launch where 1.3 GB is algorithmic, profiles/README.md).
+// The SYNC variant re-aligns them: at the start of every tile round each cluster's producer bumps a global counter and
+// waits (bounded: 20 us, then goes on -- the wait is an optimisation, never needed for correctness, so a cluster that is
+// not resident yet, e.g. behind a concurrent NCCL kernel, cannot deadlock the others) until all clusters of the round have
+// arrived.  The six buffered stages keep the tensor core busy meanwhile.  The counter is monotonic across launches
+// (sync_base = its value before this launch; launches are stream-ordered).
+__device__ unsigned long long g_gemm2_sync_ctr = 0ull;
+
+__device__ __forceinline__ void soft_grid_sync(unsigned long long* ctr, unsigned long long target) {
+  atomicAdd(ctr, 1ull);
+  const uint64_t t0 = global_timer_ns();
+  while (*reinterpret_cast<volatile unsigned long long*>(ctr) < target) {
+    if (global_timer_ns() - t0 > 20000ull) break;
+  }
+}
+
+template <int A_MN, int B_MN, bool SYNC>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmC, Gemm2Params p) {
@@ -90,7 +112,12 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (elect_one()) {  // elect.sync: the compiler keeps UTCHMMA / UTMALDG operands in uniform registers (no per-op ELECT loop)
       int stage = 0;
       uint32_t phase = 0;
+      [[maybe_unused]] int round = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        if constexpr (SYNC) {
+          ++round;
+          if (rank == 0) soft_grid_sync(p.sync_ctr, p.sync_base + static_cast<unsigned long long>(round) * num_clusters);
+        }
         int tm, tn;
         tile_coords(tile, tm, tn);
         const int m0 = tm * G2_BM + rank * 128;
@@ -117,6 +144,11 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             stage = 0;
             phase ^= 1;
           }
+        }
+      }
+      if constexpr (SYNC) {  // a cluster without a tile in the last round still arrives, so nobody waits for it
+        if (rank == 0) {
+          for (; round < p.sync_rounds; ++round) atomicAdd(p.sync_ctr, 1ull);
         }
       }
     }
@@ -264,10 +296,23 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   }
 }
 
-template <int A_MN, int B_MN>
-static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const Gemm2Params& p,
-                        cudaStream_t stream) {
-  auto kern = gemm_bf16_tcgen05_2sm<A_MN, B_MN>;
+// B200_GEMM2_SYNC=1 (K >= B200_GEMM2_SYNC_MIN_K, default 8192) selects the lock-step variant.  Written after the round-1 GPU
+// budget was spent: to be measured (ncu dram__bytes, step time) before it becomes the default.  Assumes one device per
+// process and stream-ordered GEMM launches (both true for this package).
+static bool gemm2_sync_wanted(int K) {
+  static const int min_k = [] {
+    const char* on = getenv("B200_GEMM2_SYNC");
+    if (!on || atoi(on) <= 0) return -1;
+    const char* mk = getenv("B200_GEMM2_SYNC_MIN_K");
+    return mk && atoi(mk) > 0 ? atoi(mk) : 8192;
+  }();
+  return min_k > 0 && K >= min_k;
+}
+
+template <int A_MN, int B_MN, bool SYNC>
+static int launch_gemm2_v(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, Gemm2Params p,
+                          cudaStream_t stream) {
+  auto kern = gemm_bf16_tcgen05_2sm<A_MN, B_MN, SYNC>;
   static bool attr_set = false;
   if (!attr_set) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
@@ -281,6 +326,15 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
   }
   int clusters = sms / 2;
   if (num_tiles < clusters) clusters = num_tiles;
+  if (SYNC) {
+    static unsigned long long* ctr = nullptr;
+    static unsigned long long host_base = 0ull;
+    if (!ctr) B200_CHECK_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&ctr), g_gemm2_sync_ctr));
+    p.sync_ctr = ctr;
+    p.sync_base = host_base;
+    p.sync_rounds = (num_tiles + clusters - 1) / clusters;
+    host_base += static_cast<unsigned long long>(p.sync_rounds) * clusters;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * 2);
   cfg.blockDim = dim3(G2_THREADS);
@@ -295,6 +349,13 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
   cfg.numAttrs = 1;
   B200_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, p));
   return B200_OK;
+}
+
+template <int A_MN, int B_MN>
+static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const Gemm2Params& p,
+                        cudaStream_t stream) {
+  return gemm2_sync_wanted(p.K) ? launch_gemm2_v<A_MN, B_MN, true>(tmA, tmB, tmC, p, stream)
+                                : launch_gemm2_v<A_MN, B_MN, false>(tmA, tmB, tmC, p, stream);
 }
 
 }  // namespace b200
@@ -329,6 +390,9 @@ extern "C" int b200_gemm_bf16_2sm(const void* A, const void* B, void* C, int M, 
   p.K = K;
   p.ldc = ldc;
   p.accumulate = accumulate;
+  p.sync_ctr = nullptr;
+  p.sync_base = 0ull;
+  p.sync_rounds = 0;
   // M tiles per rasterisation group (wave footprint ~ group_m x 74/group_m tiles of 256x256).  B200_GEMM2_GROUP_M overrides the
   // default for sweeps (profiles/README.md: DRAM re-reads are the open issue of this kernel).
   static const int group_m_env = [] {
