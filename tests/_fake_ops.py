@@ -221,6 +221,15 @@ def ce_bwd_sharded(logits, target_local, lse_global, row_scale):
     return (p * row_scale[:, None]).to(logits.dtype)
 
 
+def kv_append(k_new, v_new, k_cache, v_cache, offset):
+    B, H, q, D = k_new.shape
+    assert k_new.stride(3) == 1 and v_new.stride(3) == 1 and k_cache.stride() == v_cache.stride()
+    assert offset + q <= k_cache.shape[2], "append beyond the cache capacity"
+    k_cache[:, :, offset:offset + q] = k_new
+    v_cache[:, :, offset:offset + q] = v_new
+    _log("kv_append", k_new)
+
+
 # ---- optimizer: the "device pointers" of the tables are resolved through a registry of live CPU tensors
 _PTRS = {}
 
@@ -274,7 +283,7 @@ def grad_scale_(table, chunk_map, coef):
 
 
 _NAMES = ["gemm", "embedding_fwd", "embedding_bwd", "rmsnorm_fwd", "rmsnorm_bwd", "rope_", "glu_fwd", "glu_bwd", "attn_fwd",
-          "attn_bwd", "ce_fwd", "ce_bwd", "ce_row_lse", "ce_bwd_sharded", "optim_chunk_elems",
+          "attn_bwd", "ce_fwd", "ce_bwd", "ce_row_lse", "ce_bwd_sharded", "kv_append", "optim_chunk_elems",
           "adamw_step", "grad_norm", "grad_scale_"]
 
 

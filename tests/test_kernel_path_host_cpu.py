@@ -173,3 +173,53 @@ def test_packed_weights_are_parameter_views_and_survive_optimizer_steps():
     assert "qkv" not in att.__dict__["_b200_packed"]
     transformers_b200.unpack_weights(ours)
     assert "_b200_packed" not in att.__dict__
+
+
+def test_inplace_kv_cache_grows_crops_and_reorders_like_the_reference(monkeypatch):
+    """B200DynamicLayer on the kernel path (append kernel faked): prefill + decode through make_cache() must reproduce the
+    full forward, across a buffer re-allocation; crop / batch re-ordering keep the reference layer's semantics."""
+    from transformers_b200.cache import layer_class, make_cache
+
+    monkeypatch.setattr(layer_class(), "min_capacity", 4)  # force a geometric re-allocation inside the test
+    ref, ours = _pair(transformers.LlamaForCausalLM, _llama_cfg())
+    ours.eval()
+    ref.eval()
+    torch.manual_seed(8)
+    ids = torch.randint(0, 160, (2, 14))
+    with torch.no_grad():
+        full = ref(input_ids=ids).logits
+        cache = make_cache(ours.config)
+        out = ours(input_ids=ids[:, :6], past_key_values=cache, use_cache=True)
+        steps = [out.logits]
+        for t in range(6, 14):
+            steps.append(ours(input_ids=ids[:, t:t + 1], past_key_values=cache, use_cache=True).logits)
+    torch.testing.assert_close(torch.cat(steps, 1), full, atol=2e-5, rtol=1e-4)
+    layer = cache.layers[0]
+    assert type(layer) is layer_class() and layer.get_seq_length() == 14 and layer._buf_k.shape[2] == 16
+    assert [c[0] for c in _fake_ops.CALLS].count("kv_append") > 2 * 9  # appends + the copies of two re-allocations
+    keys_before = layer.keys.clone()
+    layer.crop(10)
+    assert layer.get_seq_length() == 10 and torch.equal(layer.keys, keys_before[:, :, :10])
+    layer.reorder_cache(torch.tensor([1, 0]))
+    assert torch.equal(layer.keys, keys_before[[1, 0]][:, :, :10])
+    layer.reset()
+    assert layer.get_seq_length() == 0
+
+
+def test_loss_hook_honours_num_items_in_batch_and_ignore_index():
+    """Trainer passes num_items_in_batch under gradient accumulation (loss/loss_utils.py:48-70): sum / num_items."""
+    from transformers.loss.loss_utils import ForCausalLMLoss
+
+    from transformers_b200.integration import b200_causal_lm_loss
+
+    torch.manual_seed(9)
+    logits = torch.randn(2, 10, 50, requires_grad=True)
+    labels = torch.randint(0, 50, (2, 10))
+    labels[0, 3:6] = -100
+    mine = logits.detach().clone().requires_grad_(True)
+    a = ForCausalLMLoss(logits, labels, vocab_size=50, num_items_in_batch=torch.tensor(40))
+    b = b200_causal_lm_loss(mine, labels, vocab_size=50, num_items_in_batch=torch.tensor(40))
+    torch.testing.assert_close(b, a, atol=1e-6, rtol=1e-6)
+    a.backward()
+    b.backward()
+    torch.testing.assert_close(mine.grad, logits.grad, atol=1e-7, rtol=1e-5)

@@ -54,7 +54,9 @@ def _make_layer_class():
         def update(self, key_states, value_states, *args, **kwargs):
             if not self.is_initialized:
                 self.lazy_initialization(key_states, value_states)
-            if not key_states.is_cuda or key_states.dtype != torch.bfloat16:
+            from . import modules as M
+
+            if not M._on_b200(key_states) or key_states.dtype not in M.KERNEL_DTYPES:
                 return super().update(key_states, value_states, *args, **kwargs)
             B, H, q, D = key_states.shape
             self._reserve(B, H, D, self._len + q)
