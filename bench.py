@@ -221,12 +221,31 @@ def cpu_baseline_block(seq: int = 1024):
     }
 
 
+def use_all_host_cores():
+    """torchrun exports OMP_NUM_THREADS=1 to every worker it starts (N > 1): undo that for the CPU arm, which runs on rank 0
+    alone and is meant to use every physical core of the box (hyper-threads measured 7x slower, see run_reference)."""
+    import torch
+
+    if os.environ.get("LOCAL_RANK") is None or os.environ.get("OMP_NUM_THREADS") != "1":
+        return
+    try:
+        import psutil
+
+        n = psutil.cpu_count(logical=False) or 0
+    except Exception:
+        n = 0
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    n = min(n, avail) if n else max(1, avail // 2)
+    torch.set_num_threads(max(1, n))
+
+
 def run_reference(args):
     import torch
 
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    use_all_host_cores()
     # torch's default intra-op pool (= physical cores on the GPU box): forcing os.cpu_count() hyper-threads measured 7x
     # slower (9.65 s vs 1.35 s per layer on the 64-core / 128-thread host), which would flatter the GPU arm
     seq = 1024
