@@ -129,6 +129,15 @@ int b200_grad_norm(const int64_t* tensor_table, const int32_t* chunk_map, int n_
 int b200_grad_scale(const int64_t* tensor_table, const int32_t* chunk_map, int n_chunks, const float* coef,
                     b200_stream_t stream);
 
+/* ---- tensor-parallel reduction over NVLink peer memory ---------------------------------------------
+ * The rowwise layers of the tp_plan produce partial sums that the reference all-reduces (distributed/tensor_parallel.py:
+ * 320-328).  Here every rank writes its partial into a peer-mapped buffer; after a barrier each rank pulls the rows it owns
+ * from all `world` buffers (peer_ptrs: HOST array of device pointers in rank order, own buffer included), sums them in
+ * fp32 in rank order, adds `residual` (may be NULL) and writes bf16: reduce-scatter (+ residual add) as one kernel whose
+ * loads are the NVLink transfer.  world in {1, 2, 4, 8}; offset_elems / n_elems multiples of 8. */
+int b200_pull_reduce_bf16(const void* const* peer_ptrs, int world, int64_t offset_elems, int64_t n_elems,
+                          const void* residual, void* out, b200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -282,8 +282,71 @@ def grad_scale_(table, chunk_map, coef):
     _log("grad_scale_", table)
 
 
+def pull_reduce(peer_ptrs, offset_elems, n_elems, out, residual=None):
+    acc = torch.zeros(n_elems, dtype=torch.float32)
+    if residual is not None:
+        acc += residual.reshape(-1).float()
+    for p in peer_ptrs:  # rank order, like the kernel
+        acc += _PTRS[p].reshape(-1)[offset_elems:offset_elems + n_elems].float()
+    out.copy_(acc.view(out.shape))
+    _log("pull_reduce", out)
+    return out
+
+
+class FakePeerWorkspace:
+    """Stand-in for transformers_b200.symm.PeerWorkspace over gloo: "peer-mapped" buffers are emulated by all-gathering
+    every rank's buffer at the barrier.  Checks the double-buffer protocol the real workspace relies on."""
+
+    def __init__(self, group=None, dtype=torch.float32):
+        import contextlib
+
+        import torch.distributed as dist
+
+        self.dist, self.group, self.dtype = dist, group, dtype
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self._partial, self._peers_partial, self._peers_shard = None, None, None
+        self._null = contextlib.nullcontext
+        self.ops = 0
+
+    def next_partial(self, rows, cols):
+        self._partial = torch.empty(rows, cols, dtype=self.dtype)
+        self._peers_partial = None
+        return self._partial
+
+    def _gather(self, t):
+        parts = [torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(parts, t.contiguous(), group=self.group)
+        return parts
+
+    def publish_partial(self):
+        self._peers_partial = self._gather(self._partial)
+        self.ops += 1
+
+    def partial_ptrs(self):
+        assert self._peers_partial is not None, "pull before publish_partial(): the barrier is what makes peer data visible"
+        keys = []
+        for t in self._peers_partial:
+            _PTRS[t.data_ptr()] = t
+            keys.append(t.data_ptr())
+        return keys
+
+    def publish_shard(self, local2):
+        self._peers_shard = self._gather(local2)
+        self.ops += 1
+
+    def peer_shard(self, src, rows, cols):
+        assert src != self.rank, "own rows are a local copy"
+        return self._peers_shard[src].view(rows, cols)
+
+    def copy_context(self):
+        return self._null()
+
+    def join_copies(self):
+        pass
+
+
 _NAMES = ["gemm", "embedding_fwd", "embedding_bwd", "rmsnorm_fwd", "rmsnorm_bwd", "rope_", "glu_fwd", "glu_bwd", "attn_fwd",
-          "attn_bwd", "ce_fwd", "ce_bwd", "ce_row_lse", "ce_bwd_sharded", "kv_append", "optim_chunk_elems",
+          "attn_bwd", "ce_fwd", "ce_bwd", "ce_row_lse", "ce_bwd_sharded", "kv_append", "pull_reduce", "optim_chunk_elems",
           "adamw_step", "grad_norm", "grad_scale_"]
 
 

@@ -27,7 +27,12 @@ ref_g = {n: p.grad.detach().float().clone() for n, p in model.named_parameters()
 model.zero_grad(set_to_none=True)
 SP = int(os.environ.get("B200_TP_SP", "0"))  # >0: sequence parallel with that many pipelined chunks
 VP = bool(int(os.environ.get("B200_TP_VOCAB_LOSS", "0")))  # vocabulary-parallel loss (no logits all-gather)
-tensor_parallelize(model, sequence_parallel=SP > 0, chunks=max(SP, 1), vocab_parallel_loss=VP)
+PEER = bool(int(os.environ.get("B200_TP_PEER", "0")))  # collectives over NVLink peer memory (needs B200_TP_SP>0)
+ws = None
+if PEER:
+    from transformers_b200.symm import PeerWorkspace
+    ws = PeerWorkspace(dist.group.WORLD)
+tensor_parallelize(model, sequence_parallel=SP > 0, chunks=max(SP, 1), vocab_parallel_loss=VP, peer_workspace=ws)
 out = model(input_ids=ids, labels=ids); out.loss.backward()
 if VP:
     ref_logits = ref_logits.chunk(world, dim=-1)[rank]
@@ -39,6 +44,6 @@ for n, p in model.named_parameters():
     if leaf in styles: g = g.chunk(world, dim=styles[leaf])[rank]
     worst = max(worst, ((p.grad.float() - g).abs().max() / (g.abs().max() + 1e-8)).item())
 ok = err < 5e-2 and abs(out.loss.item() - ref_loss) < 2e-2 and worst < 5e-2
-print(f"rank {rank}/{world} sp={SP} vp={int(VP)}: logits max err {err:.4f}, loss {out.loss.item():.4f} vs {ref_loss:.4f}, worst grad rel err {worst:.4f} -> {'OK' if ok else 'FAIL'}", flush=True)
+print(f"rank {rank}/{world} sp={SP} vp={int(VP)} peer={int(PEER)}: logits max err {err:.4f}, loss {out.loss.item():.4f} vs {ref_loss:.4f}, worst grad rel err {worst:.4f} -> {'OK' if ok else 'FAIL'}", flush=True)
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

@@ -70,3 +70,26 @@ def test_adamw_and_clip_kernels_match_oracle(state_dtype):
     assert abs(float(n) - total) < 1e-3 * total
     for p, gr in zip(ps, grads):
         torch.testing.assert_close(p.grad.cpu().float(), (gr.float() * coef).to(torch.bfloat16).float(), atol=1e-6, rtol=8e-3)
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_pull_reduce_kernel_on_local_buffers(world):
+    """b200_pull_reduce_bf16 with all `world` "peer" buffers on this GPU (the addressing / summation logic; the NVLink side
+    is covered by tests/cuda/tp_check.py with B200_TP_PEER=1): fp32 sum in rank order + residual, rounded once."""
+    from transformers_b200 import ops
+
+    torch.manual_seed(world)
+    rows, cols = 96, 264  # 25344 elements per rank slice: several CTAs, not a multiple of the block size
+    bufs = [torch.randn(world * rows, cols, device="cuda").to(torch.bfloat16) for _ in range(world)]
+    res = torch.randn(rows, cols, device="cuda").to(torch.bfloat16)
+    for rank in range(world):
+        sl = slice(rank * rows, (rank + 1) * rows)
+        want = res.float()
+        for b in bufs:
+            want = want + b[sl].float()
+        out = torch.empty(rows, cols, device="cuda", dtype=torch.bfloat16)
+        ops.pull_reduce([b.data_ptr() for b in bufs], rank * rows * cols, rows * cols, out, residual=res)
+        assert torch.equal(out, want.to(torch.bfloat16))
+        want0 = sum(b[sl].float() for b in bufs)
+        ops.pull_reduce([b.data_ptr() for b in bufs], rank * rows * cols, rows * cols, out)
+        assert torch.equal(out, want0.to(torch.bfloat16))

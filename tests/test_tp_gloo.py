@@ -26,7 +26,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, q, mode, sp, S=12, vp=False):
+def _worker(rank, world, port, q, mode, sp, S=12, vp=False, peer=False):
     try:
         sys.path.insert(0, ROOT)
         sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -60,11 +60,14 @@ def _worker(rank, world, port, q, mode, sp, S=12, vp=False):
         plan = resolve_plan(model)
         assert plan["model.layers.*.self_attn.q_proj"] == "colwise" and plan["model.layers.*.mlp.down_proj"] == "rowwise"
         assert plan["lm_head"] == "colwise_gather_output"
-        tensor_parallelize(model, sequence_parallel=sp, chunks=3, vocab_parallel_loss=vp)
+        ws = None
         if mode == "kernel-path":
             import _fake_ops
 
             _fake_ops.install()
+            ws = _fake_ops.FakePeerWorkspace() if peer else None
+        tensor_parallelize(model, sequence_parallel=sp, chunks=3, vocab_parallel_loss=vp, peer_workspace=ws)
+        if mode == "kernel-path":
             model.set_attn_implementation("b200")
             model.loss_function = transformers_b200.integration.b200_causal_lm_loss
         att = model.model.layers[0].self_attn
@@ -76,14 +79,16 @@ def _worker(rank, world, port, q, mode, sp, S=12, vp=False):
         out.loss.backward()
         if sp:
             st = model._b200_sp
-            assert st.active and st.full_shape == (2, S, 64) and st.chunks == 3
+            assert st.active and st.full_shape == (2, S, 64) and st.chunks == (1 if peer else 3)
+        if peer:  # 2 layers x (attention, MLP) x (entry all-gather + exit reduce-scatter) x (fwd, bwd), all over "peer memory"
+            assert ws.ops == 2 * 2 * 2 * 2 and [c[0] for c in _fake_ops.CALLS].count("pull_reduce") == 2 * 2 * 2
         if mode == "kernel-path":
             names = [c[0] for c in _fake_ops.CALLS]
             assert names.count("attn_fwd") == 2 and names.count("attn_bwd") == 2
             shapes = [c[1][0] for c in _fake_ops.CALLS if c[0] == "gemm"]
             if not sp and 2 * S >= 512:  # rowwise GEMMs (o, down) are issued in two row halves so the all-reduces overlap
                 assert sum(1 for sh in shapes if sh[0] == S) >= 2 * 2 * 2, shapes
-            if sp:  # every fused linear inside a block runs chunk by chunk: (qkv, o, gate|up, down) x (fwd, dgrad) x 3 chunks
+            if sp and not peer:  # every fused linear inside a block runs chunk by chunk: (qkv, o, gate|up, down) x (fwd, dgrad) x 3 chunks
                 assert sum(1 for sh in shapes if sh[0] == 24 // 3) == 2 * 4 * 2 * 3, shapes
         if vp:  # labels were passed: lm_head kept its vocabulary shard and the loss exchanged per-row statistics only
             assert out.logits.shape[-1] == 160 // world and "ce_bwd_sharded" in names and "ce_fwd" not in names
@@ -108,15 +113,15 @@ def _worker(rank, world, port, q, mode, sp, S=12, vp=False):
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("mode,sp,S,vp", [("stock", False, 12, False), ("stock", True, 12, False),
-                                          ("kernel-path", False, 12, False), ("kernel-path", True, 12, True),
-                                          ("kernel-path", False, 256, True)])
-def test_tp2_matches_single_process_gloo(mode, sp, S, vp):
+@pytest.mark.parametrize("mode,sp,S,vp,peer", [("stock", False, 12, False, False), ("stock", True, 12, False, False),
+                                               ("kernel-path", False, 12, False, False), ("kernel-path", True, 12, True, False),
+                                               ("kernel-path", False, 256, True, False), ("kernel-path", True, 12, False, True)])
+def test_tp2_matches_single_process_gloo(mode, sp, S, vp, peer):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q, mode, sp, S, vp)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, mode, sp, S, vp, peer)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=280) for _ in range(world)]

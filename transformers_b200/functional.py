@@ -31,11 +31,40 @@ def _tp_unpack(tp):
     return tp[0], tp[1], (tp[2] if len(tp) > 2 else None)
 
 
+def _peer_reduce_scatter(part, st):
+    """Reduce-scatter of the partial sums every rank just wrote into its peer-mapped buffer ``part`` [T, C]: barrier, then
+    one kernel pulls this rank's rows from all peers over NVLink and sums them (csrc/peer.cu).  Returns [T/N, C]."""
+    T, C = part.shape
+    rows = T // st.world
+    st.peer.publish_partial()
+    out = torch.empty(rows, C, device=part.device, dtype=part.dtype)
+    return ops.pull_reduce(st.peer.partial_ptrs(), st.rank * rows * C, rows * C, out)
+
+
+def _peer_all_gather(local2, st):
+    """All-gather of token shards over peer memory: publish the shard, barrier, then copy every peer's shard out with the
+    copy engines on a side stream (no SM time); the own rows are a local copy.  Returns [T, K]."""
+    rows, K = local2.shape
+    ws = st.peer
+    ws.publish_shard(local2)
+    full = torch.empty(rows * st.world, K, device=local2.device, dtype=local2.dtype)
+    full[st.rank * rows:(st.rank + 1) * rows].copy_(local2)
+    with ws.copy_context():
+        for i in range(1, st.world):
+            src = (st.rank + i) % st.world
+            full[src * rows:(src + 1) * rows].copy_(ws.peer_shard(src, rows, K), non_blocking=True)
+    ws.join_copies()
+    return full
+
+
 def _sp_gather_gemm(x_local2, w, st):
     """Colwise block entry under sequence parallelism: y = all_gather(x) @ w^T with the all-gather of chunk c+1 running
     on the communicator's stream while chunk c is in the GEMM.  Returns (x_full [T,K] -- kept for the wgrad --, y [T,N])."""
     from .parallel import sp_all_gather
 
+    if st.peer is not None:
+        x_full = _peer_all_gather(x_local2, st)
+        return x_full, ops.gemm(x_full, w)
     x_full, works = sp_all_gather(x_local2, st)
     y = x_full.new_empty(x_full.shape[0], w.shape[0])
     for rows, work in zip(st.chunk_rows(x_full.shape[0]), works):
@@ -51,6 +80,10 @@ def _sp_dgrad_scatter(dy2, w, st):
     from .parallel import sp_reduce_scatter_chunk
 
     T = dy2.shape[0]
+    if st.peer is not None:
+        part = st.peer.next_partial(T, w.shape[1])
+        ops.gemm(dy2, w, b_mn=True, out=part)
+        return _peer_reduce_scatter(part, st), [], None
     dx_local = dy2.new_empty(T // st.world, w.shape[1])
     works, keep = [], []
     for c, rows in enumerate(st.chunk_rows(T)):
@@ -66,6 +99,10 @@ def _sp_gemm_scatter(x2, w, st):
     from .parallel import sp_reduce_scatter_chunk
 
     T = x2.shape[0]
+    if st.peer is not None:
+        part = st.peer.next_partial(T, w.shape[0])
+        ops.gemm(x2, w, out=part)
+        return _peer_reduce_scatter(part, st)
     y_local = x2.new_empty(T // st.world, w.shape[0])
     works, keep = [], []
     for c, rows in enumerate(st.chunk_rows(T)):
@@ -82,6 +119,9 @@ def _sp_gather_dgrad(dy_local2, w, st):
     Returns (dy_full [T,N] -- for the wgrad --, dx [T,K])."""
     from .parallel import sp_all_gather
 
+    if st.peer is not None:
+        dy_full = _peer_all_gather(dy_local2, st)
+        return dy_full, ops.gemm(dy_full, w, b_mn=True)
     dy_full, works = sp_all_gather(dy_local2, st)
     dx = dy_full.new_empty(dy_full.shape[0], w.shape[1])
     for rows, work in zip(st.chunk_rows(dy_full.shape[0]), works):

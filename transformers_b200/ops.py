@@ -415,3 +415,19 @@ def grad_scale_(table: torch.Tensor, chunk_map: torch.Tensor, coef: torch.Tensor
     lib = _lib_ready()
     check(lib.b200_grad_scale(table.data_ptr(), chunk_map.data_ptr(), chunk_map.shape[0], coef.data_ptr(), _stream()),
           "b200_grad_scale")
+
+
+# ---------------------------------------------------------------------------------------------------- peer memory
+def pull_reduce(peer_ptrs: list[int], offset_elems: int, n_elems: int, out: torch.Tensor,
+                residual: torch.Tensor | None = None) -> torch.Tensor:
+    """out[i] = bf16(residual[i] + sum_s peer_s[offset + i]) where peer_ptrs are the base addresses of every rank's
+    peer-mapped partial buffer (rank order, own buffer included).  The loads are the NVLink transfer."""
+    lib = _lib_ready()
+    _chk_bf16(out, residual)
+    if not out.is_contiguous() or out.numel() != n_elems or (residual is not None and (not residual.is_contiguous() or residual.numel() != n_elems)):
+        raise B200Error("pull_reduce: out / residual must be contiguous with n_elems elements")
+    arr = (ctypes.c_void_p * len(peer_ptrs))(*peer_ptrs)
+    check(lib.b200_pull_reduce_bf16(ctypes.cast(arr, ctypes.c_void_p), len(peer_ptrs), int(offset_elems), int(n_elems),
+                                    residual.data_ptr() if residual is not None else None, out.data_ptr(), _stream()),
+          "b200_pull_reduce_bf16")
+    return out

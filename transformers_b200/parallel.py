@@ -86,13 +86,18 @@ class SequenceParallelState:
     ``active`` / ``full_shape`` describe the forward currently in flight; the first decoder layer's pre-hook sets them
     (sequence parallelism is skipped for KV-cache forwards and token counts that do not divide)."""
 
-    def __init__(self, group, chunks: int = 2):
+    def __init__(self, group, chunks: int = 2, peer=None):
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.chunks = int(chunks)
         self.active = False
         self.full_shape = None
+        # symm.PeerWorkspace: the kernel path then runs its all-gathers / reduce-scatters itself over NVLink peer memory
+        # (functional._peer_*) instead of NCCL; the layout is then one row block per rank (chunks == 1)
+        self.peer = peer
+        if peer is not None and self.chunks != 1:
+            raise ValueError("the peer-memory transport uses the plain one-block-per-rank token layout (chunks=1)")
 
     def usable(self, tokens: int) -> bool:
         return tokens > 0 and tokens % (self.world * self.chunks) == 0
@@ -311,11 +316,13 @@ def _install_vocab_parallel_loss(model: nn.Module) -> None:
 
 
 def tensor_parallelize(model: nn.Module, group=None, plan: dict | None = None, sequence_parallel: bool = False,
-                       chunks: int = 2, vocab_parallel_loss: bool = False) -> nn.Module:
+                       chunks: int = 2, vocab_parallel_loss: bool = False, peer_workspace=None) -> nn.Module:
     """Shard an already materialised model in place (each rank keeps its slice) and tell the block modules which group
     to reduce over.  Mirrors apply_tensor_parallelism (distributed/tensor_parallel.py:773-796) for colwise / rowwise /
     colwise_gather_output; embeddings and norms stay replicated.  ``sequence_parallel``: see the module docstring;
-    ``vocab_parallel_loss``: see ``_install_vocab_parallel_loss``."""
+    ``vocab_parallel_loss``: see ``_install_vocab_parallel_loss``; ``peer_workspace`` (a ``symm.PeerWorkspace``, needs
+    ``sequence_parallel``): the kernel path's all-gathers / reduce-scatters run over NVLink peer memory with our own
+    kernels instead of NCCL."""
     group = group if group is not None else dist.group.WORLD
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     plan = plan if plan is not None else resolve_plan(model)
@@ -352,7 +359,7 @@ def tensor_parallelize(model: nn.Module, group=None, plan: dict | None = None, s
             blocks.add(name)
     model.__dict__["_b200_tp_world"] = world
     if sequence_parallel and world > 1:
-        st = SequenceParallelState(group, chunks)
+        st = SequenceParallelState(group, 1 if peer_workspace is not None else chunks, peer=peer_workspace)
         for name, mod in model.named_modules():
             if name in blocks and "_b200_tp_gather" not in mod.__dict__:
                 mod.__dict__["_b200_sp"] = st
