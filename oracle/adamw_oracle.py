@@ -11,8 +11,6 @@ parameters: the oracle computes in fp32 on the loaded values and rounds once per
 torch's CPU path rounds after every elementary op -- compared within bf16 tolerance)."""
 import math
 
-import torch
-
 
 def adamw_step(p, g, m, v, step, lr, beta1, beta2, eps, weight_decay, grad_scale=1.0):
     """One update, returns new (p, m, v) in the dtypes of the inputs; arithmetic in fp32 like the kernel."""
