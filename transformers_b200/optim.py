@@ -38,6 +38,10 @@ def _tables(entries, device):
 
 
 def _check_param(p):
+    from . import modules as M
+
+    if not M._on_b200(p):
+        raise B200Error(f"B200AdamW: parameters must live on the B200 (got {p.device}); there is no CPU fallback")
     if p.dtype not in _DTYPES or not p.is_contiguous():
         raise B200Error(f"B200AdamW: parameters must be contiguous bfloat16 tensors, got {p.dtype} contiguous={p.is_contiguous()}")
     if p.grad.dtype != p.dtype or not p.grad.is_contiguous() or p.grad.is_sparse:
