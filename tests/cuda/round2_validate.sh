@@ -1,14 +1,17 @@
 #!/usr/bin/env bash
 # First GPU call of the next round: validates everything that was written after round 1's GPU budget was spent
-# (never run on a device), cheapest first.  Usage (2 GPUs, ~6 min of box time):
-#   gpurun --gpus 2 --timeout 900 -- 'bash tests/cuda/round2_validate.sh 2>&1 | tee gpurun_out/round2_validate.log'
+# (never run on a device), cheapest first.  Two parts, because a multi-GPU box is charged N x its time:
+#   gpurun --timeout 1500 -- 'PART=single bash tests/cuda/round2_validate.sh 2>&1 | tee gpurun_out/round2_single.log'
+#   gpurun --gpus 2 --timeout 900 -- 'PART=multi bash tests/cuda/round2_validate.sh 2>&1 | tee gpurun_out/round2_multi.log'
 # Every step is bounded by `timeout`; a failing step is reported and the script goes on.
 set -u
 cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 N=${N:-2}
+PART=${PART:-single}
 run() { echo "=== $*"; timeout "${T:-300}" "$@"; echo "--- exit $?"; }
 
+if [ "$PART" = single ]; then
 # 1. single-GPU kernels: vocabulary-sharded CE backward, multi-tensor AdamW / grad-norm / scale
 T=300 run env B200_EXPERIMENTAL=1 python -m pytest tests/test_experimental_gpu.py -q -m gpu
 # 2. regular suite still green on this build
@@ -17,6 +20,8 @@ T=600 run python -m pytest tests -x -q -m gpu
 T=600 run env B200_ATTN_FWD_ILP=1 python -m pytest tests/test_kernels_gpu.py tests/test_model_gpu.py -x -q -m gpu -k "attn or attention or llama"
 T=300 run python tests/cuda/bringup_attn.py
 T=300 run env B200_ATTN_FWD_ILP=1 python tests/cuda/bringup_attn.py
+fi
+if [ "$PART" = multi ]; then
 # 3. NCCL parity of the tensor-parallel variants on a tiny model (logits / loss / gradient shards vs single GPU)
 for cfg in "0 0" "2 0" "0 1" "2 1" "4 1"; do
   set -- $cfg
@@ -33,6 +38,8 @@ for flags in "" "--sequence-parallel 2" "--sequence-parallel 4" "--sequence-para
   T=300 run python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port 29612 \
     bench.py --gpus "$N" --steps 3 --warmup 3 --layers 8 --no-cpu-baseline $flags
 done
+fi
+if [ "$PART" = single ]; then
 # 5. packed weights (parameters as views of the fused buffer) on one GPU, 8 layers
 T=300 run python bench.py --steps 3 --warmup 3 --layers 8 --no-cpu-baseline --pack-weights 1
 # 6. GEMM DRAM re-reads (profiles/README.md: 2-8x the algorithmic bytes): rasterisation group size sweep under ncu
@@ -47,3 +54,4 @@ T=300 run env B200_GEMM2_SYNC=1 ncu --metrics gpu__time_duration.sum,dram__bytes
   --clock-control none -k regex:gemm_bf16 --csv --log-file gpurun_out/gemm_traffic_sync.csv python tests/cuda/prof_kernels.py gemm
 T=300 run env B200_GEMM2_SYNC=1 python bench.py --steps 3 --warmup 3 --layers 8 --no-cpu-baseline
 T=300 run python bench.py --steps 3 --warmup 3 --layers 8 --no-cpu-baseline
+fi
