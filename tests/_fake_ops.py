@@ -225,6 +225,9 @@ def kv_append(k_new, v_new, k_cache, v_cache, offset):
     B, H, q, D = k_new.shape
     assert k_new.stride(3) == 1 and v_new.stride(3) == 1 and k_cache.stride() == v_cache.stride()
     assert offset + q <= k_cache.shape[2], "append beyond the cache capacity"
+    if k_new.untyped_storage().data_ptr() == k_cache.untyped_storage().data_ptr():  # in-place move inside one buffer
+        src0 = (k_new.data_ptr() - k_cache.data_ptr()) // (k_cache.element_size() * k_cache.stride(2))
+        assert src0 >= offset + q or src0 + q <= offset, "kv_append: source and destination rows overlap (parallel copy)"
     k_cache[:, :, offset:offset + q] = k_new
     v_cache[:, :, offset:offset + q] = v_new
     _log("kv_append", k_new)

@@ -223,3 +223,50 @@ def test_loss_hook_honours_num_items_in_batch_and_ignore_index():
     a.backward()
     b.backward()
     torch.testing.assert_close(mine.grad, logits.grad, atol=1e-7, rtol=1e-5)
+
+
+def test_inplace_sliding_window_layer_matches_the_reference_layer():
+    """B200SlidingWindowLayer vs DynamicSlidingWindowLayer (cache_utils.py:203-262) on random update sequences: prefill longer
+    and shorter than the window, single-token decode across several buffer wrap-arounds, record_past + crop, beam re-order."""
+    from transformers.cache_utils import DynamicSlidingWindowLayer
+
+    from transformers_b200.cache import sliding_layer_class
+
+    g = torch.Generator().manual_seed(11)
+    for window, first in ((5, 3), (5, 12), (8, 8), (2, 1)):
+        ref, ours = DynamicSlidingWindowLayer(sliding_window=window), sliding_layer_class()(sliding_window=window)
+        for step, q in enumerate([first] + [1] * 23 + [3, 1, 1, 4, 4, 2, 4, 1]):
+            k, v = torch.randn(2, 2, q, 4, generator=g), torch.randn(2, 2, q, 4, generator=g)
+            rk, rv = ref.update(k, v)
+            ok, ov = ours.update(k, v)
+            assert torch.equal(ok, rk) and torch.equal(ov, rv), (window, step)
+            assert torch.equal(ours.keys, ref.keys) and ours.cumulative_length == ref.cumulative_length
+            assert ours.get_mask_sizes(1) == ref.get_mask_sizes(1) and ours.get_seq_length() == ref.get_seq_length()
+            if step == 10:  # the base class re-orders the batch (beam search): detected and rebuilt on the next update
+                idx = torch.tensor([1, 0])
+                ref.reorder_cache(idx)
+                ours.reorder_cache(idx)
+        assert ours._buf_k.shape[2] <= 2 * (window - 1) + max(first, 4) + 1  # bounded by window + longest update, not by the context
+    appended = [c for c in _fake_ops.CALLS if c[0] == "kv_append"]
+    assert len(appended) > 4 * 32  # every update is one append (+ occasional window moves), never a torch.cat of the window
+
+
+def test_make_cache_inplace_sliding_generates_like_the_reference_cache():
+    cfg = transformers.Gemma2Config(vocab_size=160, hidden_size=64, intermediate_size=176, num_hidden_layers=2,
+                                    num_attention_heads=4, num_key_value_heads=2, head_dim=16, sliding_window=6,
+                                    query_pre_attn_scalar=16, max_position_embeddings=128, pad_token_id=0)
+    from transformers_b200.cache import layer_class, make_cache, sliding_layer_class
+
+    ref, ours = _pair(transformers.Gemma2ForCausalLM, cfg)
+    ref.eval()
+    ours.eval()
+    torch.manual_seed(12)
+    ids = torch.randint(1, 160, (2, 20))
+    with torch.no_grad():
+        full = ref(input_ids=ids).logits
+        cache = make_cache(ours.config, inplace_sliding=True)
+        assert type(cache.layers[0]) is sliding_layer_class() and type(cache.layers[1]) is layer_class()
+        outs = [ours(input_ids=ids[:, :9], past_key_values=cache, use_cache=True).logits]
+        for t in range(9, 20):
+            outs.append(ours(input_ids=ids[:, t:t + 1], past_key_values=cache, use_cache=True).logits)
+    torch.testing.assert_close(torch.cat(outs, 1), full, atol=5e-5, rtol=1e-4)

@@ -105,7 +105,80 @@ def _make_layer_class():
     return B200DynamicLayer
 
 
+def _make_sliding_class():
+    from transformers.cache_utils import DynamicSlidingWindowLayer
+
+    class B200SlidingWindowLayer(DynamicSlidingWindowLayer):
+        """DynamicSlidingWindowLayer (cache_utils.py:203-262) without the per-token ``torch.cat`` of the whole window: K/V
+        live in a buffer of at least 2 x (window - 1) rows; ``update`` appends the new rows in place (``b200_kv_append``)
+        and returns views; the kept window just advances its start offset, and the last window - 1 rows are moved back to
+        the front (one copy per ~window tokens, regions never overlap) when the end of the buffer is reached.
+        Any manipulation the base class does on ``self.keys`` / ``self.values`` (crop, beam re-ordering, batch selection)
+        is detected on the next ``update`` and the buffer is rebuilt from them."""
+
+        def _views_are_ours(self):
+            return (self._buf_k is not None and self.keys.dim() == 4 and self.keys.shape[2] == self._n
+                    and self.keys.shape[0] == self._buf_k.shape[0]
+                    and (self._n == 0 or self.keys.data_ptr() == self._buf_k[:, :, self._s:].data_ptr()))
+
+        def update(self, key_states, value_states, *args, **kwargs):
+            from . import modules as M
+
+            if not self.is_initialized:
+                self.lazy_initialization(key_states, value_states)
+                self._buf_k = self._buf_v = None
+                self._s = self._n = 0
+            if not M._on_b200(key_states) or key_states.dtype not in M.KERNEL_DTYPES:
+                return super().update(key_states, value_states, *args, **kwargs)
+            B, H, q, D = key_states.shape
+            keep_max = self.sliding_window - 1
+            if not self._views_are_ours():  # first call, or the base class re-sliced / re-ordered keys and values
+                old_k, old_v = self.keys, self.values
+                self._n = old_k.shape[2] if old_k.dim() == 4 else 0
+                self._buf_k = self._buf_v = None
+                self._s = 0
+            else:
+                old_k = old_v = None
+            need = self._n + q
+            cap = 0 if self._buf_k is None else self._buf_k.shape[2]
+            wrap = self._buf_k is not None and need <= cap and self._s + need > cap
+            if wrap and self._s >= self._n:  # end of the buffer: move the kept rows to the front, regions do not overlap
+                if self._n > 0:
+                    ops.kv_append(self._buf_k[:, :, self._s:self._s + self._n], self._buf_v[:, :, self._s:self._s + self._n],
+                                  self._buf_k, self._buf_v, 0)
+                self._s = 0
+            elif self._buf_k is None or need > cap or wrap:  # (re)allocate: room for the window twice, or for a long prefill
+                new_cap = max(2 * keep_max + 1, need + keep_max, cap)
+                nk = torch.empty(B, H, new_cap, D, dtype=self.dtype, device=self.device)
+                nv = torch.empty(B, H, new_cap, D, dtype=self.dtype, device=self.device)
+                src_k = old_k if old_k is not None else (self._buf_k[:, :, self._s:self._s + self._n] if self._buf_k is not None else None)
+                src_v = old_v if old_v is not None else (self._buf_v[:, :, self._s:self._s + self._n] if self._buf_v is not None else None)
+                if self._n > 0:
+                    ops.kv_append(src_k, src_v, nk, nv, 0)
+                self._buf_k, self._buf_v, self._s = nk, nv, 0
+            self.cumulative_length += q
+            ops.kv_append(key_states, value_states, self._buf_k, self._buf_v, self._s + self._n)
+            full_k = self._buf_k[:, :, self._s:self._s + need]
+            full_v = self._buf_v[:, :, self._s:self._s + need]
+            keep = need if self.record_past else min(need, keep_max)
+            self._s += need - keep
+            self._n = keep
+            self.keys = self._buf_k[:, :, self._s:self._s + keep]
+            self.values = self._buf_v[:, :, self._s:self._s + keep]
+            return full_k, full_v
+
+    return B200SlidingWindowLayer
+
+
 _LAYER_CLS = None
+_SLIDING_CLS = None
+
+
+def sliding_layer_class():
+    global _SLIDING_CLS
+    if _SLIDING_CLS is None:
+        _SLIDING_CLS = _make_sliding_class()
+    return _SLIDING_CLS
 
 
 def layer_class():
@@ -115,10 +188,11 @@ def layer_class():
     return _LAYER_CLS
 
 
-def make_cache(config):
+def make_cache(config, inplace_sliding: bool = False):
     """DynamicCache(config=...) (cache_utils.py:1773-1815) with every full-attention layer replaced by B200DynamicLayer;
-    sliding-window layers keep the reference's DynamicSlidingWindowLayer."""
-    from transformers.cache_utils import DynamicCache, DynamicLayer
+    sliding-window layers keep the reference's DynamicSlidingWindowLayer unless ``inplace_sliding`` (B200SlidingWindowLayer:
+    same semantics, no per-token copy of the window; written after round 1's GPU budget, CPU-validated only)."""
+    from transformers.cache_utils import DynamicCache, DynamicLayer, DynamicSlidingWindowLayer
 
     cache = DynamicCache(config=config)
     cls = layer_class()
@@ -127,4 +201,7 @@ def make_cache(config):
         cache.layers = [cls() for _ in range(n)]
     else:
         cache.layers = [cls() if type(l) is DynamicLayer else l for l in cache.layers]
+    if inplace_sliding:
+        scls = sliding_layer_class()
+        cache.layers = [scls(sliding_window=l.sliding_window) if type(l) is DynamicSlidingWindowLayer else l for l in cache.layers]
     return cache
