@@ -221,6 +221,45 @@ def ce_bwd_sharded(logits, target_local, lse_global, row_scale):
     return (p * row_scale[:, None]).to(logits.dtype)
 
 
+def moe_route(top_k_index, E):
+    T, k = top_k_index.shape
+    flat = top_k_index.reshape(-1)
+    order = torch.sort(flat, stable=True).indices  # any order inside an expert is allowed; stable = deterministic
+    n = flat.numel()
+    slot = torch.empty(n, dtype=torch.int32)
+    slot[order] = torch.arange(n, dtype=torch.int32)
+    tok = (order // k).to(torch.int32)
+    counts = torch.bincount(flat, minlength=E)
+    offsets = torch.zeros(E + 1, dtype=torch.int32)
+    offsets[1:] = counts.cumsum(0).to(torch.int32)
+    _log("moe_route", top_k_index)
+    return offsets, slot, tok
+
+
+def moe_gather(x, tok):
+    _log("moe_gather", x)
+    return x[tok.long()].contiguous()
+
+
+def moe_combine(ys, slot, weights, T, k):
+    out = (ys[slot.long()].view(T, k, -1).float() * weights.float()[..., None]).sum(1)
+    _log("moe_combine", ys)
+    return out.to(ys.dtype)
+
+
+def moe_experts_forward(x, top_k_index, top_k_weights, gate_up, down, gelu=False):
+    E = gate_up.shape[0]
+    offsets, slot, tok = moe_route(top_k_index, E)
+    off = offsets.tolist()
+    xs = moe_gather(x, tok)
+    ys = torch.empty(xs.shape[0], x.shape[1], dtype=x.dtype)
+    for e in range(E):
+        lo, hi = off[e], off[e + 1]
+        if hi > lo:
+            ys[lo:hi] = glu_fwd(xs[lo:hi] @ gate_up[e].t(), gelu) @ down[e].t()
+    return moe_combine(ys, slot, top_k_weights, *top_k_index.shape)
+
+
 def kv_append(k_new, v_new, k_cache, v_cache, offset):
     B, H, q, D = k_new.shape
     assert k_new.stride(3) == 1 and v_new.stride(3) == 1 and k_cache.stride() == v_cache.stride()
@@ -349,7 +388,8 @@ class FakePeerWorkspace:
 
 
 _NAMES = ["gemm", "embedding_fwd", "embedding_bwd", "rmsnorm_fwd", "rmsnorm_bwd", "rope_", "glu_fwd", "glu_bwd", "attn_fwd",
-          "attn_bwd", "ce_fwd", "ce_bwd", "ce_row_lse", "ce_bwd_sharded", "kv_append", "pull_reduce", "optim_chunk_elems",
+          "attn_bwd", "ce_fwd", "ce_bwd", "ce_row_lse", "ce_bwd_sharded", "kv_append", "pull_reduce", "moe_route", "moe_gather",
+          "moe_combine", "moe_experts_forward", "optim_chunk_elems",
           "adamw_step", "grad_norm", "grad_scale_"]
 
 

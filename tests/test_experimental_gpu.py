@@ -93,3 +93,33 @@ def test_pull_reduce_kernel_on_local_buffers(world):
         want0 = sum(b[sl].float() for b in bufs)
         ops.pull_reduce([b.data_ptr() for b in bufs], rank * rows * cols, rows * cols, out)
         assert torch.equal(out, want0.to(torch.bfloat16))
+
+
+def test_mixtral_moe_backward_matches_oracle():
+    """functional.MoEExpertsFn on the GPU kernels vs the stock eager experts in fp32 on the same bf16 weights."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from _hf import import_transformers
+
+    tf = import_transformers()
+    import transformers_b200
+
+    transformers_b200.enable()
+    cfg = tf.MixtralConfig(vocab_size=256, hidden_size=256, intermediate_size=512, num_hidden_layers=1, num_attention_heads=4,
+                           num_key_value_heads=2, head_dim=64, num_local_experts=4, num_experts_per_tok=2,
+                           max_position_embeddings=256, sliding_window=None, router_jitter_noise=0.0)
+    tf.set_seed(0)
+    model = tf.MixtralForCausalLM._from_config(cfg, attn_implementation="eager", dtype=torch.bfloat16).cuda()
+    ids = torch.randint(0, 256, (2, 128), device="cuda")
+    ref = model(input_ids=ids, labels=ids)
+    ref.loss.backward()
+    g_ref = {n: p.grad.float().clone() for n, p in model.named_parameters()}
+    model.zero_grad(set_to_none=True)
+    transformers_b200.accelerate(model)
+    out = model(input_ids=ids, labels=ids)
+    out.loss.backward()
+    assert abs(out.loss.item() - ref.loss.item()) < 3e-2
+    for n, p in model.named_parameters():
+        denom = g_ref[n].abs().max().item() + 1e-6
+        assert (p.grad.float() - g_ref[n]).abs().max().item() / denom < 6e-2, n

@@ -270,3 +270,21 @@ def test_make_cache_inplace_sliding_generates_like_the_reference_cache():
         for t in range(9, 20):
             outs.append(ours(input_ids=ids[:, t:t + 1], past_key_values=cache, use_cache=True).logits)
     torch.testing.assert_close(torch.cat(outs, 1), full, atol=5e-5, rtol=1e-4)
+
+
+def test_mixtral_moe_forward_and_backward_through_the_experts_registry():
+    """config 4 family: the b200 experts entry (ExpertsInterface) under autograd = functional.MoEExpertsFn; gradients of the
+    hidden states, the router (through top_k_weights) and the stacked expert weights vs the stock eager experts."""
+    cfg = transformers.MixtralConfig(vocab_size=160, hidden_size=64, intermediate_size=96, num_hidden_layers=2,
+                                     num_attention_heads=4, num_key_value_heads=2, head_dim=16, num_local_experts=4,
+                                     num_experts_per_tok=2, max_position_embeddings=128, sliding_window=None,
+                                     router_jitter_noise=0.0, output_router_logits=False)
+    ref, ours = _pair(transformers.MixtralForCausalLM, cfg)
+    assert ours.config._experts_implementation == "b200"
+    torch.manual_seed(13)
+    ids = torch.randint(0, 160, (2, 24))
+    _compare(ref, ours, ids, atol=5e-5)
+    names = [c[0] for c in _fake_ops.CALLS]
+    assert names.count("moe_route") == 2 and names.count("moe_combine") == 2 * 2  # fwd un-permute + bwd dX per layer
+    with torch.no_grad():  # inference path (no autograd bookkeeping) gives the same logits
+        torch.testing.assert_close(ours(input_ids=ids).logits, ref(input_ids=ids).logits, atol=5e-5, rtol=1e-4)

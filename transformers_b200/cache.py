@@ -160,7 +160,7 @@ def _make_sliding_class():
             ops.kv_append(key_states, value_states, self._buf_k, self._buf_v, self._s + self._n)
             full_k = self._buf_k[:, :, self._s:self._s + need]
             full_v = self._buf_v[:, :, self._s:self._s + need]
-            keep = need if self.record_past else min(need, keep_max)
+            keep = need if getattr(self, "record_past", False) else min(need, keep_max)  # record_past: newer transformers only
             self._s += need - keep
             self._n = keep
             self.keys = self._buf_k[:, :, self._s:self._s + keep]

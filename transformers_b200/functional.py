@@ -469,3 +469,76 @@ class VocabParallelLossFn(torch.autograd.Function):
         lg, local, lse_global, valid, denom = ctx.saved_tensors
         row_scale = valid.float() * (dloss.float() / denom)
         return ops.ce_bwd_sharded(lg, local, lse_global, row_scale).view(ctx.shape), None, None, None, None, None
+
+
+class MoEExpertsFn(torch.autograd.Function):
+    """MixtralExperts.forward (models/mixtral/modeling_mixtral.py:69-93) with its backward, on the routing / gather /
+    combine kernels and per-expert GEMMs: pairs (token, k) are sorted by expert, each expert runs its gate|up and down
+    projections on its row range, the outputs are un-permuted with the routing weights.
+
+    Backward (all on the same kernels): dY_sorted = w * gather(dOut); dW_down[e] = dY_e^T act_e, dAct = dY_e down[e];
+    dGU = glu'(gu) dAct; dW_gu[e] = dGU_e^T x_e, dX_sorted = dGU_e gate_up[e]; dX = combine(dX_sorted, 1);
+    d top_k_weights[t,j] = <dOut[t], y_sorted[slot(t,j)]> (the router's gradient path)."""
+
+    @staticmethod
+    def forward(ctx, x, top_k_index, top_k_weights, gate_up, down, gelu):
+        T, H = x.shape
+        k = top_k_index.shape[1]
+        E = gate_up.shape[0]
+        offsets, slot, tok = ops.moe_route(top_k_index, E)
+        off = offsets.tolist()  # one host sync per MoE block: expert row ranges are launch parameters of the GEMMs
+        xs = ops.moe_gather(x, tok)
+        n = xs.shape[0]
+        gu = torch.empty(n, gate_up.shape[1], device=x.device, dtype=x.dtype)
+        ys = torch.empty(n, H, device=x.device, dtype=x.dtype)
+        for e in range(E):
+            lo, hi = off[e], off[e + 1]
+            if hi > lo:
+                ops.gemm(xs[lo:hi], gate_up[e], out=gu[lo:hi])
+        act = ops.glu_fwd(gu, gelu)
+        for e in range(E):
+            lo, hi = off[e], off[e + 1]
+            if hi > lo:
+                ops.gemm(act[lo:hi], down[e], out=ys[lo:hi])
+        out = ops.moe_combine(ys, slot, top_k_weights, T, k)
+        ctx.save_for_backward(xs, gu, act, ys, slot, tok, top_k_weights, gate_up, down)
+        ctx.cfg = (off, gelu, T, k)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xs, gu, act, ys, slot, tok, weights, gate_up, down = ctx.saved_tensors
+        off, gelu, T, k = ctx.cfg
+        E = gate_up.shape[0]
+        dout = dout.contiguous()
+        g = ops.moe_gather(dout, tok)  # dOut of the token behind every sorted slot
+        slot_l = slot.long()
+        dweights = None
+        if ctx.needs_input_grad[2]:
+            dots = (g.float() * ys.float()).sum(dim=-1)  # [n] row dot products (n x H elementwise: not a hot op)
+            dweights = dots[slot_l].view(T, k).to(weights.dtype)
+        w_sorted = torch.empty(slot.numel(), device=g.device, dtype=torch.float32)
+        w_sorted[slot_l] = weights.reshape(-1).float()
+        dys = (g.float() * w_sorted[:, None]).to(g.dtype)
+        dact = torch.empty_like(act)
+        d_down = torch.zeros_like(down) if ctx.needs_input_grad[4] else None
+        for e in range(E):
+            lo, hi = off[e], off[e + 1]
+            if hi > lo:
+                ops.gemm(dys[lo:hi], down[e], b_mn=True, out=dact[lo:hi])
+                if d_down is not None:
+                    ops.gemm(dys[lo:hi], act[lo:hi], a_mn=True, b_mn=True, out=d_down[e])
+        dgu = ops.glu_bwd(dact, gu, gelu)
+        dxs = torch.empty_like(xs)
+        d_gate_up = torch.zeros_like(gate_up) if ctx.needs_input_grad[3] else None
+        for e in range(E):
+            lo, hi = off[e], off[e + 1]
+            if hi > lo:
+                ops.gemm(dgu[lo:hi], gate_up[e], b_mn=True, out=dxs[lo:hi])
+                if d_gate_up is not None:
+                    ops.gemm(dgu[lo:hi], xs[lo:hi], a_mn=True, b_mn=True, out=d_gate_up[e])
+        dx = None
+        if ctx.needs_input_grad[0]:
+            ones = torch.ones(T, k, device=dxs.device, dtype=torch.float32)
+            dx = ops.moe_combine(dxs, slot, ones, T, k)
+        return dx, None, dweights, d_gate_up, d_down, None

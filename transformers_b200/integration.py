@@ -77,11 +77,10 @@ def b200_attention_mask(batch_size, q_length, kv_length, q_offset=0, kv_offset=0
 def b200_experts_forward(self, hidden_states, top_k_index, top_k_weights):
     """ExpertsInterface entry (integrations/moe.py:481-506, call site :568-570): fn(module, hidden_states [T,H],
     top_k_index [T,k] int64, top_k_weights [T,k]) -> [T,H].  The module supplies gate_up_proj [E,2I,H], down_proj [E,H,I]
-    and act_fn (MixtralExperts models/mixtral/modeling_mixtral.py:56-93).  Inference path (no autograd)."""
+    and act_fn (MixtralExperts models/mixtral/modeling_mixtral.py:56-93).  Under autograd the call goes through
+    functional.MoEExpertsFn (same kernels, with backward); without it through the allocation-lean inference path."""
     from . import ops
 
-    if torch.is_grad_enabled() and (hidden_states.requires_grad or self.gate_up_proj.requires_grad):
-        raise B200Error("b200 experts: backward through the MoE path is not implemented yet (use it under torch.no_grad())")
     if getattr(self, "is_transposed", False) or getattr(self, "has_bias", False) or not getattr(self, "has_gate", True):
         raise B200Error("b200 experts: only concatenated, untransposed, bias-free gate_up_proj experts are supported")
     act = getattr(self.config, "hidden_act", "silu")
@@ -89,7 +88,12 @@ def b200_experts_forward(self, hidden_states, top_k_index, top_k_weights):
         raise B200Error(f"b200 experts: activation {act} not supported")
     shape = hidden_states.shape
     x = hidden_states.reshape(-1, shape[-1])
-    out = ops.moe_experts_forward(x, top_k_index, top_k_weights, self.gate_up_proj, self.down_proj, act == "gelu_pytorch_tanh")
+    gelu = act == "gelu_pytorch_tanh"
+    if torch.is_grad_enabled() and (x.requires_grad or top_k_weights.requires_grad or self.gate_up_proj.requires_grad
+                                    or self.down_proj.requires_grad):
+        out = Fn.MoEExpertsFn.apply(x, top_k_index, top_k_weights, self.gate_up_proj, self.down_proj, gelu)
+    else:
+        out = ops.moe_experts_forward(x, top_k_index, top_k_weights, self.gate_up_proj, self.down_proj, gelu)
     return out.view(shape)
 
 

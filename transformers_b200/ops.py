@@ -314,6 +314,45 @@ def moe_experts_forward(x: torch.Tensor, top_k_index: torch.Tensor, top_k_weight
     return out
 
 
+def moe_route(top_k_index: torch.Tensor, E: int):
+    """top_k_index [T,k] int64 -> (offsets int32 [E+1], slot int32 [T*k] position of pair (t,j) in expert-sorted order,
+    tok int32 [T*k] token of every sorted slot)."""
+    lib = _lib_ready()
+    T, k = top_k_index.shape
+    dev, n = top_k_index.device, T * k
+    idx = top_k_index.contiguous().to(torch.int64)
+    counts = torch.zeros(E, device=dev, dtype=torch.int32)
+    offsets = torch.empty(E + 1, device=dev, dtype=torch.int32)
+    cursor = torch.empty(E, device=dev, dtype=torch.int32)
+    slot = torch.empty(n, device=dev, dtype=torch.int32)
+    tok = torch.empty(n, device=dev, dtype=torch.int32)
+    check(lib.b200_moe_route(idx.data_ptr(), counts.data_ptr(), offsets.data_ptr(), cursor.data_ptr(), slot.data_ptr(),
+                             tok.data_ptr(), T, k, E, _stream()), "b200_moe_route")
+    return offsets, slot, tok
+
+
+def moe_gather(x: torch.Tensor, tok: torch.Tensor) -> torch.Tensor:
+    """rows x[tok[s]] -> [n, H]"""
+    lib = _lib_ready()
+    _chk_bf16(x)
+    x = x.contiguous()
+    n, H = tok.numel(), x.shape[1]
+    xs = torch.empty(n, H, device=x.device, dtype=BF16)
+    check(lib.b200_moe_gather(x.data_ptr(), tok.data_ptr(), xs.data_ptr(), n, H, _stream()), "b200_moe_gather")
+    return xs
+
+
+def moe_combine(ys: torch.Tensor, slot: torch.Tensor, weights: torch.Tensor, T: int, k: int) -> torch.Tensor:
+    """out[t] = sum_j weights[t,j] * ys[slot[t*k+j]]  ([T, H] bf16; weights fp32 [T,k])"""
+    lib = _lib_ready()
+    _chk_bf16(ys)
+    H = ys.shape[1]
+    w = weights.contiguous().to(torch.float32)
+    out = torch.empty(T, H, device=ys.device, dtype=BF16)
+    check(lib.b200_moe_combine(ys.data_ptr(), slot.data_ptr(), w.data_ptr(), out.data_ptr(), T, k, H, _stream()), "b200_moe_combine")
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------------- loss
 def ce_fwd(logits: torch.Tensor, labels: torch.Tensor, shift: bool = True, ignore_index: int = -100,
            num_items: float | None = None):
