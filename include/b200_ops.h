@@ -27,6 +27,10 @@ const char* b200_last_error(void);     /* thread-local message of the last faili
  * D[M,N] (+)= sum_k A(m,k) B(n,k); a_mn/b_mn = 0: operand stored [M|N, K]; 1: stored [K, M|N].  tcgen05 + TMA. */
 int b200_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
                    int b_mn, int accumulate, b200_stream_t stream);
+/* decode rows, 1 <= M <= 4: y[M,N] = x[M,K] W[N,K]^T as one stream over W (HBM-bound: CUDA cores, one warp per output
+ * column); b200_gemm_bf16 dispatches to it for such shapes when B200_GEMV=1 */
+int b200_gemv_bf16(const void* x, const void* W, void* y, int M, int N, int K, int ldx, int ldw, int ldy,
+                   b200_stream_t stream);
 /* CTA-pair variant (tcgen05 cta_group::2, 256x256 tile per 2-CTA cluster); b200_gemm_bf16 dispatches to it for M > 128 */
 int b200_gemm_bf16_2sm(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
                        int b_mn, int accumulate, b200_stream_t stream);

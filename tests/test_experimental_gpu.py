@@ -123,3 +123,33 @@ def test_mixtral_moe_backward_matches_oracle():
     for n, p in model.named_parameters():
         denom = g_ref[n].abs().max().item() + 1e-6
         assert (p.grad.float() - g_ref[n]).abs().max().item() / denom < 6e-2, n
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 4096, 4096), (1, 6144, 3584), (4, 28672, 4096), (3, 1000, 14336), (2, 128256, 4096), (1, 7, 264)])
+def test_gemv_decode_rows_match_matmul(M, N, K):
+    """b200_gemv_bf16 (direct C-ABI call) vs fp32 matmul on the same bf16 operands; then timing against the bytes of W."""
+    import ctypes
+
+    from transformers_b200 import _lib
+
+    lib = _lib.load()
+    torch.manual_seed(M * 7 + N)
+    x = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
+    y = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    st = torch.cuda.current_stream().cuda_stream
+    rc = lib.b200_gemv_bf16(x.data_ptr(), w.data_ptr(), y.data_ptr(), M, N, K, K, K, N, ctypes.c_void_p(st))
+    assert rc == 0, _lib.last_error()
+    ref = x.float() @ w.float().t()
+    torch.testing.assert_close(y.float(), ref, atol=2e-2, rtol=1.6e-2)
+    if N * K >= 4096 * 4096:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(3):
+            lib.b200_gemv_bf16(x.data_ptr(), w.data_ptr(), y.data_ptr(), M, N, K, K, K, N, ctypes.c_void_p(st))
+        e0.record()
+        for _ in range(10):
+            lib.b200_gemv_bf16(x.data_ptr(), w.data_ptr(), y.data_ptr(), M, N, K, K, K, N, ctypes.c_void_p(st))
+        e1.record()
+        torch.cuda.synchronize()
+        gbs = N * K * 2 / (e0.elapsed_time(e1) / 10 * 1e-3) / 1e9
+        print(f"gemv M={M} N={N} K={K}: {gbs:.0f} GB/s of weight stream")

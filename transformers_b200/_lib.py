@@ -20,6 +20,7 @@ SIGNATURES = {
     "b200_device_check": [],
     "b200_last_error": [],
     "b200_gemm_bf16": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "b200_gemv_bf16": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "b200_gemm_bf16_2sm": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "b200_gemm_bf16_ex": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "b200_embedding_fwd": [_p, _p, _p, _i, _i, _i, _f, _i, _p, _p],

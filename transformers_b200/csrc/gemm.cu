@@ -298,12 +298,24 @@ extern "C" int b200_gemm_bf16_2sm(const void* A, const void* B, void* C, int M, 
 // Dispatcher.  Measured on the full Llama-3-8B step under the 1 kW power cap (profiles/README.md): the CTA-pair kernel
 // (gemm2.cu, 256x256 tiles, 32 KB/stage/SM) sustains 1453 TF/s vs 1351 TF/s for the 1-CTA 128x256 kernel, so it is the
 // default for anything taller than one tile; B200_GEMM_1SM=1 forces the 1-CTA kernel (A/B timing, tiny shapes use it anyway).
+extern "C" int b200_gemv_bf16(const void* x, const void* W, void* y, int M, int N, int K, int ldx, int ldw, int ldy,
+                              cudaStream_t stream);
+
 extern "C" int b200_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
                               int a_mn, int b_mn, int accumulate, cudaStream_t stream) {
   static const int force_1sm = [] {
     const char* e = getenv("B200_GEMM_1SM");
     return (e && e[0] == '1') ? 1 : 0;
   }();
+  // decode rows (M <= 4): stream the weights with the CUDA-core kernel of gemv.cu instead of a mostly empty tensor-core tile
+  // (B200_GEMV=1; written after the round-1 GPU budget was spent -- opt-in until it has run on a device)
+  static const int use_gemv = [] {
+    const char* e = getenv("B200_GEMV");
+    return (e && e[0] == '1') ? 1 : 0;
+  }();
+  if (use_gemv && M >= 1 && M <= 4 && !a_mn && !b_mn && !accumulate && K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0)
+    return b200_gemv_bf16(A, B, C, M, N, K, lda, ldb, ldc, stream);
   if (!force_1sm && M > 128 && N > 64)
     return b200_gemm_bf16_2sm(A, B, C, M, N, K, lda, ldb, ldc, a_mn, b_mn, accumulate, stream);
   return b200_gemm_bf16_ex(A, B, C, M, N, K, lda, ldb, ldc, a_mn, b_mn, accumulate, 0, stream);
