@@ -83,3 +83,23 @@ def test_bench_reference_arm_times_stock_layer_even_after_enable(monkeypatch):
     assert kind == "reference" and "stock transformers" in what
     monkeypatch.setenv("B200_BENCH_ORACLE_BASELINE", "1")
     assert bench.cpu_sample(seq=16, repeats=0)[2] == "port"
+
+
+def test_c_abi_validates_new_entry_points_without_a_gpu():
+    import ctypes
+
+    from transformers_b200 import _lib
+
+    lib = _lib.load()
+    assert lib.b200_gemv_bf16(None, None, None, 5, 64, 64, 64, 64, 64, None) == -22 and "1..4" in _lib.last_error()
+    assert lib.b200_gemv_bf16(None, None, None, 1, 64, 60, 64, 64, 64, None) == -22  # K % 8
+    ptrs = (ctypes.c_void_p * 3)(16, 32, 48)
+    assert lib.b200_pull_reduce_bf16(ctypes.cast(ptrs, ctypes.c_void_p), 3, 0, 64, None, ctypes.c_void_p(64), None) == -22
+    assert "not instantiated" in _lib.last_error()
+    assert lib.b200_pull_reduce_bf16(ctypes.cast(ptrs, ctypes.c_void_p), 2, 4, 64, None, ctypes.c_void_p(64), None) == -22  # offset % 8
+    assert lib.b200_adamw_step(None, None, 1, 0, 1e-3, 0.9, 0.999, 1e-8, 0.0, 0.0, 1.0, None, None) == -22  # step 0: bc1 == 0
+    assert "bias corrections" in _lib.last_error()
+    assert lib.b200_adamw_step(None, None, 0, 0, 1e-3, 0.9, 0.999, 1e-8, 0.0, 0.1, 0.03, None, None) == 0  # empty group: no launch
+    assert lib.b200_grad_scale(None, None, -1, None, None) == -22
+    assert lib.b200_ce_bwd_sharded(None, None, None, None, None, 4, 64, 60, 64, None) == -22  # ld % 8
+    assert lib.b200_optim_chunk_elems() == 32768
