@@ -70,6 +70,8 @@ def parse():
     ap.add_argument("--tp-transport", default=os.environ.get("B200_TP_TRANSPORT", "nccl"), choices=["nccl", "peer"],
                     help="tp + sequence-parallel only: 'peer' runs the all-gathers / reduce-scatters with our own kernels and "
                          "copy-engine pulls over NVLink peer memory (symmetric allocations) instead of NCCL")
+    ap.add_argument("--fuse-residual", type=int, default=int(os.environ.get("B200_FUSE_RESIDUAL", "0")),
+                    help="decoder layers run their residual adds on our kernels (first one fused with the post-attention RMSNorm)")
     ap.add_argument("--pack-weights", type=int, default=int(os.environ.get("B200_PACK_WEIGHTS", "0")),
                     help="make q/k/v and gate/up weights row views of one buffer (no second fused copy in HBM)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -342,7 +344,7 @@ def run_b200(args):
     transformers.set_seed(42)
     with torch.device("cuda"):
         model = transformers.LlamaForCausalLM._from_config(cfg, attn_implementation="b200", dtype=torch.bfloat16)
-    transformers_b200.accelerate(model)
+    transformers_b200.accelerate(model, fuse_residual=bool(args.fuse_residual))
     model.train()
     if parallelism == "tp":
         from transformers_b200.parallel import tensor_parallelize

@@ -93,6 +93,11 @@ def rope_(qkv, cos, sin, n_rot_heads, head_dim, backward=False):
     return qkv
 
 
+def add(a, b):
+    _log("add", a)
+    return a + b
+
+
 def _act(g, gelu):
     return F.gelu(g, approximate="tanh") if gelu else F.silu(g)
 
@@ -388,7 +393,7 @@ class FakePeerWorkspace:
 
 
 _NAMES = ["gemm", "embedding_fwd", "embedding_bwd", "rmsnorm_fwd", "rmsnorm_bwd", "rope_", "glu_fwd", "glu_bwd", "attn_fwd",
-          "attn_bwd", "ce_fwd", "ce_bwd", "ce_row_lse", "ce_bwd_sharded", "kv_append", "pull_reduce", "moe_route", "moe_gather",
+          "attn_bwd", "ce_fwd", "ce_bwd", "ce_row_lse", "ce_bwd_sharded", "add", "kv_append", "pull_reduce", "moe_route", "moe_gather",
           "moe_combine", "moe_experts_forward", "optim_chunk_elems",
           "adamw_step", "grad_norm", "grad_scale_"]
 

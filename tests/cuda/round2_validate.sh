@@ -44,6 +44,8 @@ fi
 if [ "$PART" = single ]; then
 # 5. packed weights (parameters as views of the fused buffer) on one GPU, 8 layers
 T=300 run python bench.py --steps 3 --warmup 3 --layers 8 --no-cpu-baseline --pack-weights 1
+# 5b. residual adds on our kernels (fused add + RMSNorm decoder layer)
+T=300 run python bench.py --steps 3 --warmup 3 --layers 8 --no-cpu-baseline --fuse-residual 1
 # 6. GEMM DRAM re-reads (profiles/README.md: 2-8x the algorithmic bytes): rasterisation group size sweep under ncu
 #    (one GPU; ncu numbers are for traffic only, never a bench value)
 for gm in 2 4 8 16 32; do

@@ -288,3 +288,24 @@ def test_mixtral_moe_forward_and_backward_through_the_experts_registry():
     assert names.count("moe_route") == 2 and names.count("moe_combine") == 2 * 2  # fwd un-permute + bwd dX per layer
     with torch.no_grad():  # inference path (no autograd bookkeeping) gives the same logits
         torch.testing.assert_close(ours(input_ids=ids).logits, ref(input_ids=ids).logits, atol=5e-5, rtol=1e-4)
+
+
+def test_fused_residual_decoder_layer_matches_the_stock_layer():
+    """accelerate(model, fuse_residual=True): residual add + post-attention RMSNorm in one kernel, second add on ours."""
+    for cls, cfg in ((transformers.LlamaForCausalLM, _llama_cfg()),
+                     (transformers.MistralForCausalLM,
+                      transformers.MistralConfig(vocab_size=160, hidden_size=64, intermediate_size=176, num_hidden_layers=2,
+                                                 num_attention_heads=4, num_key_value_heads=2, head_dim=16, sliding_window=8,
+                                                 max_position_embeddings=128))):
+        ref, ours = _pair(cls, cfg)
+        transformers_b200.accelerate(ours, fuse_residual=True)
+        assert type(ours.model.layers[0]).__name__.startswith("B200")
+        torch.manual_seed(14)
+        _compare(ref, ours, torch.randint(0, 160, (2, 20)))
+        names = [c[0] for c in _fake_ops.CALLS]
+        # per layer: forward 1 add (the other is inside rmsnorm_fwd), backward 1 add (dr + dx of the fused norm)
+        assert names.count("add") == 2 * 2 and names.count("rmsnorm_fwd") == 2 * 2 + 1
+    ours.gradient_checkpointing_enable()
+    ours.train()
+    ref.train()
+    _compare(ref, ours, torch.randint(0, 160, (2, 20)))

@@ -232,6 +232,37 @@ class RMSNormFn(torch.autograd.Function):
         return dx if _needs(ctx, 0) else None, dw if _needs(ctx, 1) else None, None, None
 
 
+class AddRMSNormFn(torch.autograd.Function):
+    """r = x + residual; y = RMSNorm(r) in ONE pass over the row (LlamaDecoderLayer.forward models/llama/modeling_llama.py:
+    317-321 does `residual + hidden_states` and `post_attention_layernorm` as two).  Returns (r, y)."""
+
+    @staticmethod
+    def forward(ctx, x, residual, weight, eps, gemma):
+        y, rstd, r = ops.rmsnorm_fwd(x, weight, eps, gemma, residual=residual)
+        ctx.save_for_backward(r, weight, rstd)
+        ctx.gemma = gemma
+        return r, y
+
+    @staticmethod
+    def backward(ctx, dr, dy):
+        r, weight, rstd = ctx.saved_tensors
+        dxn, dw = ops.rmsnorm_bwd(dy.contiguous(), r, weight, rstd, ctx.gemma)
+        d = ops.add(dr, dxn) if dr is not None else dxn  # both addends of r receive the same gradient
+        return d, d, (dw if _needs(ctx, 2) else None), None, None
+
+
+class AddFn(torch.autograd.Function):
+    """a + b on our kernel (the second residual add of the decoder layer, :323)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        return ops.add(a, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
 class GluFn(torch.autograd.Function):
     """act(gate) * up on the packed [.., 2I] projection output (LlamaMLP.forward :174-176)."""
 

@@ -170,9 +170,12 @@ def b200_causal_lm_loss(logits, labels, vocab_size=None, num_items_in_batch=None
     return Fn.CausalLMLossFn.apply(logits, labels, ignore_index, num_items_in_batch, shift)
 
 
-def accelerate(model: nn.Module, attn: bool = True, head_and_loss: bool = True, pack_weights: bool = False) -> nn.Module:
+def accelerate(model: nn.Module, attn: bool = True, head_and_loss: bool = True, pack_weights: bool = False,
+               fuse_residual: bool = False) -> nn.Module:
     """Convert an already constructed reference model in place (class swap, parameters untouched).
-    ``pack_weights``: additionally make q/k/v and gate/up weights row views of one buffer (modules.pack_weights)."""
+    ``pack_weights``: additionally make q/k/v and gate/up weights row views of one buffer (modules.pack_weights).
+    ``fuse_residual``: Llama / Mistral decoder layers run their residual adds on our kernels, the first fused with the
+    post-attention RMSNorm (modules.B200DecoderLayerMixin; CPU-validated, GPU run pending)."""
     enable()
     cmap = _class_map()
     by_base = {cls.__mro__[2]: cls for cls in cmap.values()}  # (B200X, mixin, base, ...)
@@ -199,4 +202,8 @@ def accelerate(model: nn.Module, attn: bool = True, head_and_loss: bool = True, 
                 c._experts_implementation_internal = ATTN_NAME
     if pack_weights:
         M.pack_weights(model)
+    if fuse_residual:
+        for mod in model.modules():
+            if type(mod).__name__ in ("LlamaDecoderLayer", "MistralDecoderLayer"):
+                mod.__class__ = M.make_class(type(mod), M.B200DecoderLayerMixin)
     return model

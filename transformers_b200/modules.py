@@ -210,6 +210,32 @@ class B200AttentionMixin:
         return out, None
 
 
+class B200DecoderLayerMixin:
+    """LlamaDecoderLayer / MistralDecoderLayer.forward (models/llama/modeling_llama.py:295-324) with the two residual adds on
+    our kernels: the first fused with the post-attention RMSNorm (one pass over the row instead of two), the second a plain
+    vectorised add.  Only installed by ``accelerate(model, fuse_residual=True)``; anything unexpected defers to the stock
+    forward."""
+
+    def forward(self, hidden_states, attention_mask=None, position_ids=None, past_key_values=None, use_cache=False,
+                position_embeddings=None, **kwargs):
+        norm2 = self.post_attention_layernorm
+        if not _on_b200(hidden_states) or not isinstance(norm2, B200RMSNormMixin) or hidden_states.dtype not in KERNEL_DTYPES:
+            return super().forward(hidden_states, attention_mask=attention_mask, position_ids=position_ids,
+                                   past_key_values=past_key_values, use_cache=use_cache,
+                                   position_embeddings=position_embeddings, **kwargs)
+        residual = hidden_states
+        hidden_states = self.input_layernorm(hidden_states)
+        hidden_states, _ = self.self_attn(hidden_states=hidden_states, attention_mask=attention_mask, position_ids=position_ids,
+                                          past_key_values=past_key_values, use_cache=use_cache,
+                                          position_embeddings=position_embeddings, **kwargs)
+        eps = getattr(norm2, "variance_epsilon", None)
+        if eps is None:
+            eps = norm2.eps
+        residual, hidden_states = Fn.AddRMSNormFn.apply(hidden_states, residual, _local(norm2.weight), eps, norm2._b200_gemma)
+        hidden_states = self.mlp(hidden_states)
+        return Fn.AddFn.apply(residual, hidden_states)
+
+
 class B200EmbeddingMixin:
     def forward(self, input_ids):  # nn.Embedding.forward; Gemma2TextScaledWordEmbedding models/gemma2/modeling_gemma2.py:348
         w = _local(self.weight)
