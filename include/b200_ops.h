@@ -113,6 +113,17 @@ int b200_ce_bwd(const void* logits, const int64_t* labels, const float* lse, con
 int b200_ce_bwd_sharded(const void* logits, const int64_t* target_local, const float* lse_global,
                         const float* row_scale, void* dlogits, int T, int V, int ld, int ld_out, b200_stream_t stream);
 
+/* Decode step (q_len == 1 over the KV cache; models/llama/modeling_llama.py:243-281 with past_key_values): the context is
+ * split over b200_attn_decode_splits(B, Hkv, Skv) CTAs per (batch, kv head), every K / V byte is read once and shared by the
+ * Hq / Hkv query heads; a second kernel merges the partial softmax states.  q / out: [B, 1, Hq, D] (batch, head strides);
+ * k / v: [B, Skv, Hkv, D] strided; workspace: B * Hq * nsplit * (D + 2) floats; lse (optional): [B, Hq, lse_stride], entry 0.
+ * causal masking is implied (the query is the last position); window / kv_start / kv_end as in b200_attn_fwd. */
+int b200_attn_decode_splits(int B, int Hkv, int Skv);
+int b200_attn_decode(const void* q, const void* k, const void* v, void* out, float* lse, int lse_stride, float* workspace,
+                     int B, int Skv, int Hq, int Hkv, int D, int64_t q_bs, int64_t q_hs, int64_t k_bs, int64_t k_rs,
+                     int64_t k_hs, int64_t v_bs, int64_t v_rs, int64_t v_hs, int64_t o_bs, int64_t o_hs, float scale,
+                     float softcap, int window, const int* kv_start, const int* kv_end, b200_stream_t stream);
+
 /* ---- optimizer step after the path ---------------------------------------------------------------
  * Trainer clips the global gradient norm (trainer.py:1783-1785, _clip_grad_norm :2538-2542 -> torch.nn.utils.clip_grad_norm_)
  * and calls optimizer.step() (:1788) on torch.optim.AdamW (trainer_optimizer.py:201-208).  Multi-tensor, one launch per

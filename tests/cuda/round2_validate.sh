@@ -14,8 +14,8 @@ run() { echo "=== $*"; timeout "${T:-300}" "$@"; echo "--- exit $?"; }
 if [ "$PART" = single ]; then
 # 1. single-GPU kernels: vocabulary-sharded CE backward, multi-tensor AdamW / grad-norm / scale
 T=300 run env B200_EXPERIMENTAL=1 python -m pytest tests/test_experimental_gpu.py -q -m gpu -s
-# 1b. decode path with the GEMV dispatch on: generate() parity tests
-T=600 run env B200_GEMV=1 python -m pytest tests/test_model_gpu.py -x -q -m gpu -k "generate or cache or decode"
+# 1b. decode path with the GEMV and split-context attention dispatch on: generate() parity tests
+T=600 run env B200_GEMV=1 B200_DECODE_ATTN=1 python -m pytest tests/test_model_gpu.py -x -q -m gpu -k "generate or cache or decode"
 # 2. regular suite still green on this build
 T=600 run python -m pytest tests -x -q -m gpu
 # 2b. attention forward softmax variant (batched TMEM loads, split max / sum chains): parity, then timing next to the default

@@ -153,3 +153,46 @@ def test_gemv_decode_rows_match_matmul(M, N, K):
         torch.cuda.synchronize()
         gbs = N * K * 2 / (e0.elapsed_time(e1) / 10 * 1e-3) / 1e9
         print(f"gemv M={M} N={N} K={K}: {gbs:.0f} GB/s of weight stream")
+
+
+@pytest.mark.parametrize("B,Hq,Hkv,D,ctx,window,softcap", [
+    (1, 16, 8, 256, 8704, 0, 50.0),     # Gemma-2-9B full layer at the config-5 context
+    (1, 16, 8, 256, 4095, 4096, 50.0),  # its sliding layers (cropped cache)
+    (4, 32, 8, 128, 1000, 0, 0.0),      # Llama-3-8B heads
+    (2, 8, 8, 64, 257, 0, 0.0), (3, 8, 1, 128, 300, 128, 0.0), (1, 4, 2, 128, 1, 0, 0.0), (2, 4, 4, 64, 255, 0, 30.0),
+])
+def test_decode_attention_matches_fp32_reference(B, Hq, Hkv, D, ctx, window, softcap, monkeypatch):
+    """b200_attn_decode (split-context kernel pair) on a KV-cache-shaped buffer [B, Hkv, capacity, D] vs an fp32 softmax
+    reference and vs the prefill kernel (q_len == 1 through b200_attn_fwd), including left padding."""
+    from transformers_b200 import ops
+
+    torch.manual_seed(ctx + D)
+    cap = ctx + 37
+    kc = torch.randn(B, Hkv, cap, D, device="cuda").to(torch.bfloat16)
+    vc = torch.randn(B, Hkv, cap, D, device="cuda").to(torch.bfloat16)
+    q = torch.randn(B, 1, Hq, D, device="cuda").to(torch.bfloat16)
+    k = kc[:, :, :ctx].transpose(1, 2)  # [B, ctx, Hkv, D] strided view, as the attention entry point passes it
+    v = vc[:, :, :ctx].transpose(1, 2)
+    kv_start = torch.tensor([0] + [5] * (B - 1), device="cuda", dtype=torch.int32) if ctx > 8 else None
+    scale = D ** -0.5
+    monkeypatch.setattr(ops, "_DECODE_ATTN", False)
+    out_ref_kernel, lse_ref_kernel = ops.attn_fwd(q, k, v, scale=scale, causal=False, window=window, softcap=softcap, kv_start=kv_start)
+    monkeypatch.setattr(ops, "_DECODE_ATTN", True)
+    out, lse = ops.attn_fwd(q, k, v, scale=scale, causal=False, window=window, softcap=softcap, kv_start=kv_start)
+    G = Hq // Hkv
+    kf = k.float().repeat_interleave(G, dim=2)
+    vf = v.float().repeat_interleave(G, dim=2)
+    s = torch.einsum("bhd,bkhd->bhk", q[:, 0].float(), kf) * scale
+    if softcap:
+        s = softcap * torch.tanh(s / softcap)
+    idx = torch.arange(ctx, device="cuda")
+    valid = torch.ones(B, ctx, dtype=torch.bool, device="cuda")
+    if window:
+        valid &= idx[None] >= ctx - window
+    if kv_start is not None:
+        valid &= idx[None] >= kv_start[:, None]
+    s = s.masked_fill(~valid[:, None], float("-inf"))
+    want = torch.einsum("bhk,bkhd->bhd", torch.softmax(s, -1), vf)
+    torch.testing.assert_close(out[:, 0].float(), want, atol=2e-2, rtol=2e-2)
+    torch.testing.assert_close(lse[..., 0], torch.logsumexp(s, -1), atol=2e-3, rtol=1e-3)
+    torch.testing.assert_close(out.float(), out_ref_kernel.float(), atol=2e-2, rtol=2e-2)

@@ -7,6 +7,7 @@ return code.  There is deliberately no CPU or library fallback.
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
@@ -17,7 +18,7 @@ from ._lib import check as _check
 BF16 = torch.bfloat16
 
 # kernels launched per C-ABI entry point
-_KERNELS_PER_CALL = {"b200_rmsnorm_bwd": 2, "b200_ce_fwd": 2, "b200_attn_bwd": 3, "b200_moe_route": 3, "b200_grad_norm": 2}
+_KERNELS_PER_CALL = {"b200_attn_decode": 2, "b200_rmsnorm_bwd": 2, "b200_ce_fwd": 2, "b200_attn_bwd": 3, "b200_moe_route": 3, "b200_grad_norm": 2}
 
 
 def check(rc: int, what: str) -> None:
@@ -216,6 +217,11 @@ def _bsh_strides(t: torch.Tensor):
     return t.stride(0), t.stride(1), t.stride(2)
 
 
+# B200_DECODE_ATTN=1: route q_len == 1 through the split-context decode kernel (written after round 1's GPU budget was
+# spent; opt-in until it has run on a device)
+_DECODE_ATTN = os.environ.get("B200_DECODE_ATTN", "0") == "1"
+
+
 def _lse_stride(sq: int) -> int:
     return (sq + 127) // 128 * 128
 
@@ -231,6 +237,18 @@ def attn_fwd(q, k, v, *, scale: float, causal: bool, window: int = 0, softcap: f
         out = torch.empty(B, Sq, Hq, D, device=q.device, dtype=BF16)
     ls = _lse_stride(Sq)
     lse = torch.empty(B, Hq, ls, device=q.device, dtype=torch.float32)
+    if Sq == 1 and _DECODE_ATTN and Hq // Hkv in (1, 2, 4, 8):
+        # decode step: split-context CUDA-core kernel (attention_decode.cu) instead of a 1/128-full tensor-core q tile
+        nsplit = lib.b200_attn_decode_splits(B, Hkv, Skv)
+        ws = torch.empty(B * Hq * nsplit * (D + 2), device=q.device, dtype=torch.float32)
+        kb, kr, kh = _bsh_strides(k)
+        vb, vr, vh = _bsh_strides(v)
+        check(lib.b200_attn_decode(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(), ls, ws.data_ptr(),
+                                   B, Skv, Hq, Hkv, D, q.stride(0), q.stride(2), kb, kr, kh, vb, vr, vh, out.stride(0),
+                                   out.stride(2), float(scale), float(softcap or 0.0), int(window or 0),
+                                   kv_start.data_ptr() if kv_start is not None else None,
+                                   kv_end.data_ptr() if kv_end is not None else None, _stream()), "b200_attn_decode")
+        return out, lse
     check(lib.b200_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(), ls, B, Sq, Skv, Hq, Hkv, D,
                             *_bsh_strides(q), *_bsh_strides(k), *_bsh_strides(v), *_bsh_strides(out), float(scale),
                             float(softcap or 0.0), int(causal), int(window or 0),
