@@ -309,3 +309,19 @@ def test_fused_residual_decoder_layer_matches_the_stock_layer():
     ours.train()
     ref.train()
     _compare(ref, ours, torch.randint(0, 160, (2, 20)))
+
+
+def test_gemma_v1_blocks_run_on_the_kernel_path():
+    """modeling_gemma (north star: "modeling_llama/mistral/gemma"): Llama structure + (1 + w) RMSNorm + GeGLU + scaled
+    embeddings (the scaling is reference code in GemmaModel.forward)."""
+    cfg = transformers.GemmaConfig(vocab_size=160, hidden_size=64, intermediate_size=176, num_hidden_layers=2,
+                                   num_attention_heads=4, num_key_value_heads=1, head_dim=16, max_position_embeddings=128,
+                                   pad_token_id=0)
+    ref, ours = _pair(transformers.GemmaForCausalLM, cfg)
+    layer = ours.model.layers[0]
+    assert type(layer.self_attn).__name__ == "B200GemmaAttention" and type(layer.mlp).__name__ == "B200GemmaMLP"
+    assert type(layer.input_layernorm).__name__ == "B200GemmaRMSNorm" and layer.input_layernorm._b200_gemma
+    torch.manual_seed(15)
+    _compare(ref, ours, torch.randint(1, 160, (2, 20)), atol=5e-5)
+    names = [c[0] for c in _fake_ops.CALLS]
+    assert names.count("attn_fwd") == 2 and names.count("glu_fwd") == 2

@@ -115,7 +115,19 @@ def _build_class_map() -> dict:
     from transformers.models.mixtral import modeling_mixtral as mx
 
     mk = M.make_class
+    extra = {}
+    try:  # Gemma (v1): Llama block structure with the (1 + w) norm and a GeGLU MLP
+        from transformers.models.gemma import modeling_gemma as g1
+
+        extra = {
+            "GemmaRMSNorm": mk(g1.GemmaRMSNorm, M.B200RMSNormMixin, _b200_gemma=True),
+            "GemmaMLP": mk(g1.GemmaMLP, M.B200MLPMixin),
+            "GemmaAttention": mk(g1.GemmaAttention, M.B200AttentionMixin),
+        }
+    except ImportError:  # pragma: no cover
+        pass
     return {
+        **extra,
         "LlamaRMSNorm": mk(ll.LlamaRMSNorm, M.B200RMSNormMixin),
         "LlamaMLP": mk(ll.LlamaMLP, M.B200MLPMixin),
         "LlamaAttention": mk(ll.LlamaAttention, M.B200AttentionMixin),
