@@ -39,7 +39,7 @@ class DecoderConfig:
     rope_type: str = "default"
     rope_extra: dict = field(default_factory=dict)  # llama3: factor, low/high_freq_factor, original_max_position_embeddings
     hidden_act: str = "silu"  # or "gelu_pytorch_tanh"
-    model_type: str = "llama"  # llama | mistral | gemma2
+    model_type: str = "llama"  # llama | mistral | mixtral | gemma | gemma2
     sliding_window: int | None = None
     layer_types: list | None = None  # per layer "full_attention" | "sliding_attention"
     attn_logit_softcapping: float | None = None
@@ -52,7 +52,14 @@ class DecoderConfig:
 
     @property
     def gemma(self) -> bool:
+        """Gemma-2 block structure: four norms per layer, softcaps, query_pre_attn_scalar (models/gemma2/modeling_gemma2.py)."""
         return self.model_type == "gemma2"
+
+    @property
+    def gemma_norm(self) -> bool:
+        """(1 + w) RMSNorm in fp32 and sqrt(hidden)-scaled embeddings: Gemma (models/gemma/modeling_gemma.py:64-79, :374)
+        and Gemma-2 (models/gemma2/modeling_gemma2.py:49-63, :386-389)."""
+        return self.model_type in ("gemma", "gemma2")
 
     @property
     def scaling(self) -> float:
@@ -292,24 +299,24 @@ def decoder_layer(x: torch.Tensor, p: dict, layer_idx: int, cfg: DecoderConfig, 
     """LlamaDecoderLayer.forward models/llama/modeling_llama.py:295-324; Gemma2DecoderLayer.forward
     models/gemma2/modeling_gemma2.py:304-335 (post-norms applied before each residual add)."""
     pre = f"model.layers.{layer_idx}."
-    eps, g = cfg.rms_norm_eps, cfg.gemma
+    eps, g, gn = cfg.rms_norm_eps, cfg.gemma, cfg.gemma_norm
     residual = x
-    h = rms_norm(x, p[pre + "input_layernorm.weight"], eps, g)
+    h = rms_norm(x, p[pre + "input_layernorm.weight"], eps, gn)
     h = attention_block(h, p, pre + "self_attn.", cfg, cos, sin, mask)
     if g:
-        h = rms_norm(h, p[pre + "post_attention_layernorm.weight"], eps, g)
+        h = rms_norm(h, p[pre + "post_attention_layernorm.weight"], eps, gn)
     h = residual + h
     residual = h
     if g:
-        h = rms_norm(h, p[pre + "pre_feedforward_layernorm.weight"], eps, g)
+        h = rms_norm(h, p[pre + "pre_feedforward_layernorm.weight"], eps, gn)
     else:
-        h = rms_norm(h, p[pre + "post_attention_layernorm.weight"], eps, g)
+        h = rms_norm(h, p[pre + "post_attention_layernorm.weight"], eps, gn)
     if cfg.num_local_experts:
         h = moe_block(h, p, pre + "mlp.", cfg)
     else:
         h = mlp(h, p[pre + "mlp.gate_proj.weight"], p[pre + "mlp.up_proj.weight"], p[pre + "mlp.down_proj.weight"], cfg.hidden_act)
     if g:
-        h = rms_norm(h, p[pre + "post_feedforward_layernorm.weight"], eps, g)
+        h = rms_norm(h, p[pre + "post_feedforward_layernorm.weight"], eps, gn)
     return residual + h
 
 
@@ -320,7 +327,7 @@ def model_forward(ids: torch.Tensor, p: dict, cfg: DecoderConfig, labels: torch.
     B, S = ids.shape
     w_emb = p["model.embed_tokens.weight"]
     dtype = w_emb.dtype
-    scale = cfg.hidden_size**0.5 if cfg.gemma else None
+    scale = cfg.hidden_size**0.5 if cfg.gemma_norm else None
     h = embedding(ids, w_emb, scale, cfg.pad_token_id)
     position_ids = torch.arange(S)[None, :]
     cos, sin = rope_tables(rope_inv_freq(cfg), position_ids, dtype)
@@ -330,7 +337,7 @@ def model_forward(ids: torch.Tensor, p: dict, cfg: DecoderConfig, labels: torch.
         if win not in masks:
             masks[win] = eager_mask(B, S, S, dtype, sliding_window=win, padding_mask=padding_mask)
         h = decoder_layer(h, p, li, cfg, cos, sin, masks[win])
-    h = rms_norm(h, p["model.norm.weight"], cfg.rms_norm_eps, cfg.gemma)
+    h = rms_norm(h, p["model.norm.weight"], cfg.rms_norm_eps, cfg.gemma_norm)
     w_head = w_emb if cfg.tie_word_embeddings else p["lm_head.weight"]
     logits = F.linear(h, w_head)
     if cfg.final_logit_softcapping is not None:

@@ -20,7 +20,7 @@ import torch  # noqa: E402
 import transformers  # noqa: E402
 
 assert transformers.__file__.startswith(REF), transformers.__file__
-from transformers import Gemma2Config, Gemma2ForCausalLM, LlamaConfig, LlamaForCausalLM, MistralConfig, MistralForCausalLM, MixtralConfig, MixtralForCausalLM, set_seed  # noqa: E402
+from transformers import Gemma2Config, Gemma2ForCausalLM, GemmaConfig, GemmaForCausalLM, LlamaConfig, LlamaForCausalLM, MistralConfig, MistralForCausalLM, MixtralConfig, MixtralForCausalLM, set_seed  # noqa: E402
 from transformers.models.llama import modeling_llama as ml  # noqa: E402
 from transformers.models.gemma2 import modeling_gemma2 as mg  # noqa: E402
 
@@ -164,6 +164,9 @@ if __name__ == "__main__":
                 vocab_size=160, hidden_size=64, intermediate_size=96, num_hidden_layers=2, num_attention_heads=4,
                 num_key_value_heads=2, head_dim=16, num_local_experts=4, num_experts_per_tok=2, sliding_window=None,
                 rms_norm_eps=1e-5, rope_parameters={"rope_type": "default", "rope_theta": 10000.0}), dtype),
+            "gemma1_tiny": lambda: model_fixture(f"gemma1_tiny_{tag}", GemmaForCausalLM, GemmaConfig(
+                vocab_size=160, hidden_size=64, intermediate_size=176, num_hidden_layers=2, num_attention_heads=4,
+                num_key_value_heads=1, head_dim=32, rope_parameters={"rope_type": "default", "rope_theta": 10000.0}), dtype),
             "gemma2_tiny": lambda: model_fixture(f"gemma2_tiny_{tag}", Gemma2ForCausalLM, Gemma2Config(
                 vocab_size=160, hidden_size=64, intermediate_size=176, num_hidden_layers=2, num_attention_heads=4,
                 num_key_value_heads=2, head_dim=32, sliding_window=8, query_pre_attn_scalar=32,

@@ -91,7 +91,7 @@ def test_masks_match_reference(ops):
     assert torch.equal(O.eager_mask(2, 10, 10, m.dtype, sliding_window=4), ops["mask_sliding4"].expand(2, 1, 10, 10))
 
 
-MODELS = ["llama_tiny", "llama_tiny_padded", "llama3rope_tiny", "mistral_tiny", "gemma2_tiny", "mixtral_tiny"]
+MODELS = ["llama_tiny", "llama_tiny_padded", "llama3rope_tiny", "mistral_tiny", "gemma1_tiny", "gemma2_tiny", "mixtral_tiny"]
 
 
 @pytest.mark.parametrize("tag", ["fp32", "bf16"])
