@@ -196,3 +196,43 @@ def test_decode_attention_matches_fp32_reference(B, Hq, Hkv, D, ctx, window, sof
     torch.testing.assert_close(out[:, 0].float(), want, atol=2e-2, rtol=2e-2)
     torch.testing.assert_close(lse[..., 0], torch.logsumexp(s, -1), atol=2e-3, rtol=1e-3)
     torch.testing.assert_close(out.float(), out_ref_kernel.float(), atol=2e-2, rtol=2e-2)
+
+
+def test_gemma_v1_forward_backward_matches_oracle():
+    """Gemma (v1) through the plugin ((1+w) norm, GeGLU, scaled embeddings, tied head) vs the oracle, like the regular
+    tests/test_model_gpu.py cases (opt-in only because the class-map entries were added without a GPU)."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from _hf import import_transformers
+    from oracle import decoder_oracle as O
+
+    tf = import_transformers()
+    import transformers_b200
+
+    transformers_b200.enable()
+    cfg = tf.GemmaConfig(vocab_size=512, hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
+                         num_key_value_heads=1, head_dim=64, max_position_embeddings=512,
+                         rope_parameters={"rope_type": "default", "rope_theta": 10000.0})
+    tf.set_seed(42)
+    model = tf.GemmaForCausalLM._from_config(cfg, attn_implementation="b200", dtype=torch.bfloat16)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    ocfg = O.config_from_hf(cfg)
+    ids = torch.randint(1, cfg.vocab_size, (2, 200))
+    p32 = {k: v.float().requires_grad_(True) for k, v in sd.items()}
+    lo32, loss32, _ = O.model_forward(ids, p32, ocfg, labels=ids)
+    loss32.backward()
+    with torch.no_grad():
+        lobf, _, _ = O.model_forward(ids, {k: v.clone() for k, v in sd.items()}, ocfg, labels=ids)
+    model = model.cuda().train()
+    transformers_b200.accelerate(model)
+    assert type(model.model.layers[0].mlp).__name__ == "B200GemmaMLP"
+    out = model(input_ids=ids.cuda(), labels=ids.cuda())
+    out.loss.backward()
+    got = out.logits.float().cpu()
+    torch.testing.assert_close(got, lobf.float(), atol=3e-2, rtol=3e-2)
+    assert (got - lo32.detach()).abs().max() <= 2 * (lobf.float() - lo32.detach()).abs().max() + 1e-2
+    assert abs(out.loss.item() - loss32.item()) < 3e-2
+    for n, p in model.named_parameters():
+        g32 = p32[n].grad
+        assert (p.grad.float().cpu() - g32).abs().max() / (g32.abs().max() + 1e-6) < 6e-2, n
