@@ -67,9 +67,10 @@ def parse():
     ap.add_argument("--vocab-parallel-loss", type=int, default=int(os.environ.get("B200_TP_VOCAB_LOSS", "0")),
                     help="tp only: keep lm_head's output vocabulary-sharded and exchange per-row loss statistics instead of "
                          "all-gathering the logits")
-    ap.add_argument("--tp-transport", default=os.environ.get("B200_TP_TRANSPORT", "nccl"), choices=["nccl", "peer"],
+    ap.add_argument("--tp-transport", default=os.environ.get("B200_TP_TRANSPORT", "nccl"), choices=["nccl", "peer", "peer-scatter"],
                     help="tp + sequence-parallel only: 'peer' runs the all-gathers / reduce-scatters with our own kernels and "
-                         "copy-engine pulls over NVLink peer memory (symmetric allocations) instead of NCCL")
+                         "copy-engine pulls over NVLink peer memory (symmetric allocations) instead of NCCL; 'peer-scatter' additionally lets the rowwise GEMM's epilogue store every tile "
+                         "into its owner's buffer (GEMM + transfer in one kernel)")
     ap.add_argument("--fuse-residual", type=int, default=int(os.environ.get("B200_FUSE_RESIDUAL", "0")),
                     help="decoder layers run their residual adds on our kernels (first one fused with the post-attention RMSNorm)")
     ap.add_argument("--pack-weights", type=int, default=int(os.environ.get("B200_PACK_WEIGHTS", "0")),
@@ -350,12 +351,12 @@ def run_b200(args):
         from transformers_b200.parallel import tensor_parallelize
 
         peer_ws = None
-        if args.tp_transport == "peer":
+        if args.tp_transport != "nccl":
             if args.sequence_parallel <= 0:
-                raise SystemExit("--tp-transport peer needs --sequence-parallel 1")
+                raise SystemExit("--tp-transport peer / peer-scatter needs --sequence-parallel 1")
             from transformers_b200.symm import PeerWorkspace
 
-            peer_ws = PeerWorkspace(dist.group.WORLD)
+            peer_ws = PeerWorkspace(dist.group.WORLD, scatter_epilogue=args.tp_transport == "peer-scatter")
         tensor_parallelize(model, dist.group.WORLD, sequence_parallel=args.sequence_parallel > 0,
                            chunks=max(args.sequence_parallel, 1), vocab_parallel_loss=bool(args.vocab_parallel_loss),
                            peer_workspace=peer_ws)
@@ -449,7 +450,7 @@ def run_b200(args):
                        "global_batch": B * replicas, "seq_len": S, "parallelism": (f"{parallelism}{world}" + (f"+sp{args.sequence_parallel}" if parallelism == "tp" and args.sequence_parallel > 0
                                                                  else "")
                                        + ("+vocab-parallel-loss" if parallelism == "tp" and args.vocab_parallel_loss else "")
-                                       + ("+peer-memory" if parallelism == "tp" and args.tp_transport == "peer" else "")) if world > 1 else "single",
+                                       + (f"+{args.tp_transport}" if parallelism == "tp" and args.tp_transport != "nccl" else "")) if world > 1 else "single",
                        "l2": "working set (16 GB weights + activations) >> 126 MB L2; no explicit flush needed",
                        "lm_head_and_loss": "included (b200 GEMM + fused CE kernels)"},
             "loss": float(loss.detach()), "model_tflops_per_gpu": per_gpu_tf,

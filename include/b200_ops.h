@@ -150,6 +150,13 @@ int b200_grad_scale(const int64_t* tensor_table, const int32_t* chunk_map, int n
  * from all `world` buffers (peer_ptrs: HOST array of device pointers in rank order, own buffer included), sums them in
  * fp32 in rank order, adds `residual` (may be NULL) and writes bf16: reduce-scatter (+ residual add) as one kernel whose
  * loads are the NVLink transfer.  world in {1, 2, 4, 8}; offset_elems / n_elems multiples of 8. */
+/* GEMM + first half of the reduce-scatter in ONE kernel: D = A B^T as b200_gemm_bf16 (CTA-pair tcgen05 kernel), but the
+ * epilogue TMA-stores row block r of the output (M / world rows, a multiple of 256) straight into dest_ptrs[r] (HOST array
+ * of device pointers: for r != rank a slot in rank r's peer-mapped memory), other ranks' blocks first, so the partial sums
+ * cross NVLink tile by tile under the tensor-core work of the following tiles.  Then: barrier, b200_pull_reduce_bf16 over the
+ * `world` local slots. */
+int b200_gemm_bf16_scatter(const void* A, const void* B, void* const* dest_ptrs, int world, int rank, int M, int N, int K,
+                           int lda, int ldb, int ldc, int a_mn, int b_mn, b200_stream_t stream);
 int b200_pull_reduce_bf16(const void* const* peer_ptrs, int world, int64_t offset_elems, int64_t n_elems,
                           const void* residual, void* out, b200_stream_t stream);
 

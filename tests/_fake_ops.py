@@ -340,12 +340,24 @@ def pull_reduce(peer_ptrs, offset_elems, n_elems, out, residual=None):
     return out
 
 
+def gemm_scatter(a, b, dest_ptrs, rank, *, a_mn=False, b_mn=False):
+    r = (a.t() if a_mn else a) @ (b if b_mn else b.t())
+    rows = r.shape[0] // len(dest_ptrs)
+    assert rows % 256 == 0, "scatter epilogue: whole 256-row tiles per owner"
+    for o, key in enumerate(dest_ptrs):
+        _PTRS[key].copy_(r[o * rows:(o + 1) * rows])
+    _log("gemm_scatter", a, b)
+
+
 class FakePeerWorkspace:
     """Stand-in for transformers_b200.symm.PeerWorkspace over gloo: "peer-mapped" buffers are emulated by all-gathering
     every rank's buffer at the barrier.  Checks the double-buffer protocol the real workspace relies on."""
 
-    def __init__(self, group=None, dtype=torch.float32):
+    def __init__(self, group=None, dtype=torch.float32, scatter_epilogue=False):
         import contextlib
+
+        self.scatter_epilogue = scatter_epilogue
+        self._outbox = None
 
         import torch.distributed as dist
 
@@ -365,8 +377,25 @@ class FakePeerWorkspace:
         self.dist.all_gather(parts, t.contiguous(), group=self.group)
         return parts
 
+    def next_staging(self, rows, cols):
+        # outbox[r] = what this rank's GEMM epilogue writes into rank r's slot; delivered at the barrier below
+        self._outbox = torch.zeros(self.world, rows, cols, dtype=self.dtype)
+        self._slots = None
+        dest = []
+        for r in range(self.world):
+            _PTRS[self._outbox[r].data_ptr()] = self._outbox[r]
+            dest.append(self._outbox[r].data_ptr())
+        self._slot_keys = [("slot", id(self), s) for s in range(self.world)]
+        return dest, self._slot_keys
+
     def publish_partial(self):
-        self._peers_partial = self._gather(self._partial)
+        if self._outbox is not None:  # scatter epilogue: emulate the NVLink stores with an all-to-all of the outboxes
+            boxes = self._gather(self._outbox)  # boxes[src][dst]
+            for s in range(self.world):
+                _PTRS[self._slot_keys[s]] = boxes[s][self.rank].contiguous()
+            self._outbox = None
+        else:
+            self._peers_partial = self._gather(self._partial)
         self.ops += 1
 
     def partial_ptrs(self):
@@ -393,7 +422,7 @@ class FakePeerWorkspace:
 
 
 _NAMES = ["gemm", "embedding_fwd", "embedding_bwd", "rmsnorm_fwd", "rmsnorm_bwd", "rope_", "glu_fwd", "glu_bwd", "attn_fwd",
-          "attn_bwd", "ce_fwd", "ce_bwd", "ce_row_lse", "ce_bwd_sharded", "add", "kv_append", "pull_reduce", "moe_route", "moe_gather",
+          "attn_bwd", "ce_fwd", "ce_bwd", "ce_row_lse", "ce_bwd_sharded", "add", "kv_append", "pull_reduce", "gemm_scatter", "moe_route", "moe_gather",
           "moe_combine", "moe_experts_forward", "optim_chunk_elems",
           "adamw_step", "grad_norm", "grad_scale_"]
 

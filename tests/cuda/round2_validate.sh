@@ -33,8 +33,12 @@ done
 # 3b. peer-memory transport (symmetric allocations, our pull-reduce kernel + copy-engine gathers instead of NCCL)
 T=240 run env B200_TP_SP=1 B200_TP_PEER=1 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" \
   --master-addr 127.0.0.1 --master-port 29613 tests/cuda/tp_check.py
-T=300 run python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port 29614 \
-  bench.py --gpus "$N" --steps 3 --warmup 3 --layers 8 --no-cpu-baseline --sequence-parallel 1 --tp-transport peer
+T=240 run env B200_TP_SP=1 B200_TP_PEER=2 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" \
+  --master-addr 127.0.0.1 --master-port 29615 tests/cuda/tp_check.py
+for tr in peer peer-scatter; do
+  T=300 run python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port 29614 \
+    bench.py --gpus "$N" --steps 3 --warmup 3 --layers 8 --no-cpu-baseline --sequence-parallel 1 --tp-transport $tr
+done
 # 4. what the variants buy at the real shapes (8 of 32 layers: relative numbers only, NOT a bench value)
 for flags in "" "--sequence-parallel 2" "--sequence-parallel 4" "--sequence-parallel 2 --vocab-parallel-loss 1"; do
   T=300 run python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port 29612 \

@@ -14,24 +14,24 @@ torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
 dist.init_process_group("nccl")
 transformers_b200.enable()
 cfg = tf.LlamaConfig(vocab_size=1024, hidden_size=512, intermediate_size=1024, num_hidden_layers=2, num_attention_heads=8,
-                     num_key_value_heads=8, head_dim=64, max_position_embeddings=512, use_cache=False,
+                     num_key_value_heads=8, head_dim=64, max_position_embeddings=2048, use_cache=False,
                      rope_parameters={"rope_type": "default", "rope_theta": 10000.0})
 tf.set_seed(0)
 model = tf.LlamaForCausalLM._from_config(cfg, attn_implementation="b200", dtype=torch.bfloat16).cuda()
 transformers_b200.accelerate(model)
 torch.manual_seed(1)
-ids = torch.randint(0, 1024, (2, 256), device="cuda")
+ids = torch.randint(0, 1024, (2, 256 * max(1, world // 2)), device="cuda")  # T / world stays a multiple of 256 (scatter epilogue)
 ref = model(input_ids=ids, labels=ids); ref.loss.backward()
 ref_logits, ref_loss = ref.logits.detach().float().clone(), ref.loss.item()
 ref_g = {n: p.grad.detach().float().clone() for n, p in model.named_parameters()}
 model.zero_grad(set_to_none=True)
 SP = int(os.environ.get("B200_TP_SP", "0"))  # >0: sequence parallel with that many pipelined chunks
 VP = bool(int(os.environ.get("B200_TP_VOCAB_LOSS", "0")))  # vocabulary-parallel loss (no logits all-gather)
-PEER = bool(int(os.environ.get("B200_TP_PEER", "0")))  # collectives over NVLink peer memory (needs B200_TP_SP>0)
+PEER = int(os.environ.get("B200_TP_PEER", "0"))  # 1: collectives over NVLink peer memory, 2: + GEMM scatter epilogue (needs B200_TP_SP>0)
 ws = None
 if PEER:
     from transformers_b200.symm import PeerWorkspace
-    ws = PeerWorkspace(dist.group.WORLD)
+    ws = PeerWorkspace(dist.group.WORLD, scatter_epilogue=PEER == 2)
 tensor_parallelize(model, sequence_parallel=SP > 0, chunks=max(SP, 1), vocab_parallel_loss=VP, peer_workspace=ws)
 out = model(input_ids=ids, labels=ids); out.loss.backward()
 if VP:

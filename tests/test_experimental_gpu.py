@@ -236,3 +236,24 @@ def test_gemma_v1_forward_backward_matches_oracle():
     for n, p in model.named_parameters():
         g32 = p32[n].grad
         assert (p.grad.float().cpu() - g32).abs().max() / (g32.abs().max() + 1e-6) < 6e-2, n
+
+
+@pytest.mark.parametrize("world,layout", [(2, "nt"), (4, "nt"), (4, "nn"), (8, "nt")])
+def test_gemm_scatter_epilogue_on_local_buffers(world, layout):
+    """b200_gemm_bf16_scatter with all destination slots on this GPU: every row block must land in its slot bit-identical to
+    the plain GEMM's rows (same kernel, only the TMA-store target differs)."""
+    from transformers_b200 import ops
+
+    torch.manual_seed(world)
+    rows, N, K = 256, 384, 512
+    M = rows * world
+    a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    b = (torch.randn(N, K, device="cuda") * 0.1).to(torch.bfloat16)
+    b_mn = layout == "nn"
+    bb = b.t().contiguous() if b_mn else b  # [K, N] storage for the dgrad layout
+    want = ops.gemm(a, bb, b_mn=b_mn)
+    for rank in range(world):
+        slots = torch.full((world, rows, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+        ops.gemm_scatter(a, bb, [slots[r].data_ptr() for r in range(world)], rank, b_mn=b_mn)
+        torch.cuda.synchronize()
+        assert torch.equal(slots.view(M, N), want), (world, rank)

@@ -65,7 +65,7 @@ def _worker(rank, world, port, q, mode, sp, S=12, vp=False, peer=False):
             import _fake_ops
 
             _fake_ops.install()
-            ws = _fake_ops.FakePeerWorkspace() if peer else None
+            ws = _fake_ops.FakePeerWorkspace(scatter_epilogue=(peer == "scatter")) if peer else None
         tensor_parallelize(model, sequence_parallel=sp, chunks=3, vocab_parallel_loss=vp, peer_workspace=ws)
         if mode == "kernel-path":
             model.set_attn_implementation("b200")
@@ -82,6 +82,7 @@ def _worker(rank, world, port, q, mode, sp, S=12, vp=False, peer=False):
             assert st.active and st.full_shape == (2, S, 64) and st.chunks == (1 if peer else 3)
         if peer:  # 2 layers x (attention, MLP) x (entry all-gather + exit reduce-scatter) x (fwd, bwd), all over "peer memory"
             assert ws.ops == 2 * 2 * 2 * 2 and [c[0] for c in _fake_ops.CALLS].count("pull_reduce") == 2 * 2 * 2
+            assert [c[0] for c in _fake_ops.CALLS].count("gemm_scatter") == (2 * 2 * 2 if peer == "scatter" else 0)
         if mode == "kernel-path":
             names = [c[0] for c in _fake_ops.CALLS]
             assert names.count("attn_fwd") == 2 and names.count("attn_bwd") == 2
@@ -115,7 +116,8 @@ def _worker(rank, world, port, q, mode, sp, S=12, vp=False, peer=False):
 @pytest.mark.timeout(300)
 @pytest.mark.parametrize("mode,sp,S,vp,peer", [("stock", False, 12, False, False), ("stock", True, 12, False, False),
                                                ("kernel-path", False, 12, False, False), ("kernel-path", True, 12, True, False),
-                                               ("kernel-path", False, 256, True, False), ("kernel-path", True, 12, False, True)])
+                                               ("kernel-path", False, 256, True, False), ("kernel-path", True, 12, False, True),
+                                               ("kernel-path", True, 256, False, "scatter")])
 def test_tp2_matches_single_process_gloo(mode, sp, S, vp, peer):
     world = 2
     ctx = mp.get_context("spawn")

@@ -48,6 +48,7 @@ SIGNATURES = {
     "b200_adamw_step": [_p, _p, _i, _i, _f, _f, _f, _f, _f, _f, _f, _p, _p],
     "b200_grad_norm": [_p, _p, _i, _p, _f, _p, _p],
     "b200_grad_scale": [_p, _p, _i, _p, _p],
+    "b200_gemm_bf16_scatter": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "b200_pull_reduce_bf16": [_p, _i, _l, _l, _p, _p, _p],
 }
 _RESTYPES = {"b200_last_error": c_char_p}

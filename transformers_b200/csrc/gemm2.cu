@@ -34,7 +34,15 @@ struct Gemm2Params {
   unsigned long long* sync_ctr;
   unsigned long long sync_base;
   int sync_rounds;
+  // SCATTER variant only: row block r (rows_per_owner rows) of the output goes to scatter_maps[r] (tensor maps in global
+  // memory, one per destination buffer -- peer-mapped memory of rank r); m_rot rotates the tile order so that the blocks
+  // of the other ranks are produced (and travel over NVLink) first, the own block last
+  const CUtensorMap* scatter_maps;
+  int rows_per_owner;
+  int m_rot;
 };
+
+constexpr int G2_MODE_PLAIN = 0, G2_MODE_SYNC = 1, G2_MODE_SCATTER = 2;
 
 // Co-running tiles share A row panels / B column panels through L2 only while they walk K together.  Nothing keeps the
 // 74 persistent clusters in step: after a few tiles their start times have drifted by more than L2 can bridge and the
@@ -54,7 +62,7 @@ __device__ __forceinline__ void soft_grid_sync(unsigned long long* ctr, unsigned
   }
 }
 
-template <int A_MN, int B_MN, bool SYNC>
+template <int A_MN, int B_MN, int MODE>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmC, Gemm2Params p) {
@@ -97,6 +105,8 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  constexpr bool SYNC = MODE == G2_MODE_SYNC;
+  constexpr bool SCATTER = MODE == G2_MODE_SCATTER;
 
   auto tile_coords = [&](int tile, int& tm, int& tn) {
     const int group_size = p.group_m * num_n;
@@ -106,6 +116,10 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int in_group = tile - group * group_size;
     tm = first_m + in_group % gsz;
     tn = in_group / gsz;
+    if constexpr (SCATTER) {
+      tm += p.m_rot;
+      if (tm >= num_m) tm -= num_m;
+    }
   };
 
   if (warp == 0) {
@@ -229,7 +243,12 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&tmC, sbuf, tn * G2_BN + c * 64, row0);
+            if constexpr (SCATTER) {  // the 32-row strip lives in exactly one owner's buffer (rows_per_owner % 256 == 0)
+              const int owner = row0 / p.rows_per_owner;
+              tma_store_2d(p.scatter_maps + owner, sbuf, tn * G2_BN + c * 64, row0 - owner * p.rows_per_owner);
+            } else {
+              tma_store_2d(&tmC, sbuf, tn * G2_BN + c * 64, row0);
+            }
             tma_store_commit();
           }
         }
@@ -309,10 +328,11 @@ static bool gemm2_sync_wanted(int K) {
   return min_k > 0 && K >= min_k;
 }
 
-template <int A_MN, int B_MN, bool SYNC>
+template <int A_MN, int B_MN, int MODE>
 static int launch_gemm2_v(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, Gemm2Params p,
                           cudaStream_t stream) {
-  auto kern = gemm_bf16_tcgen05_2sm<A_MN, B_MN, SYNC>;
+  constexpr bool SYNC = MODE == G2_MODE_SYNC;
+  auto kern = gemm_bf16_tcgen05_2sm<A_MN, B_MN, MODE>;
   static bool attr_set = false;
   if (!attr_set) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
@@ -354,15 +374,16 @@ static int launch_gemm2_v(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
 template <int A_MN, int B_MN>
 static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const Gemm2Params& p,
                         cudaStream_t stream) {
-  return gemm2_sync_wanted(p.K) ? launch_gemm2_v<A_MN, B_MN, true>(tmA, tmB, tmC, p, stream)
-                                : launch_gemm2_v<A_MN, B_MN, false>(tmA, tmB, tmC, p, stream);
+  if (p.scatter_maps) return launch_gemm2_v<A_MN, B_MN, G2_MODE_SCATTER>(tmA, tmB, tmC, p, stream);
+  return gemm2_sync_wanted(p.K) ? launch_gemm2_v<A_MN, B_MN, G2_MODE_SYNC>(tmA, tmB, tmC, p, stream)
+                                : launch_gemm2_v<A_MN, B_MN, G2_MODE_PLAIN>(tmA, tmB, tmC, p, stream);
 }
 
 }  // namespace b200
 
-// Same contract as b200_gemm_bf16 (gemm.cu); requires M > 128 to be worthwhile.  Called by the dispatcher there.
-extern "C" int b200_gemm_bf16_2sm(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
-                                  int a_mn, int b_mn, int accumulate, cudaStream_t stream) {
+static int gemm2_run(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
+                     int b_mn, int accumulate, const CUtensorMap* scatter_maps, int rows_per_owner, int m_rot,
+                     cudaStream_t stream) {
   using namespace b200;
   B200_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   B200_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % 8 == 0, "gemm: C must be 16B aligned, ldc %% 8 == 0");
@@ -393,6 +414,9 @@ extern "C" int b200_gemm_bf16_2sm(const void* A, const void* B, void* C, int M, 
   p.sync_ctr = nullptr;
   p.sync_base = 0ull;
   p.sync_rounds = 0;
+  p.scatter_maps = scatter_maps;
+  p.rows_per_owner = rows_per_owner;
+  p.m_rot = m_rot;
   // M tiles per rasterisation group (wave footprint ~ group_m x 74/group_m tiles of 256x256).  B200_GEMM2_GROUP_M overrides the
   // default for sweeps (profiles/README.md: DRAM re-reads are the open issue of this kernel).
   static const int group_m_env = [] {
@@ -410,4 +434,60 @@ extern "C" int b200_gemm_bf16_2sm(const void* A, const void* B, void* C, int M, 
   if (!a_mn && b_mn) return launch_gemm2<0, 1>(tmA, tmB, tmC, p, stream);
   if (a_mn && b_mn) return launch_gemm2<1, 1>(tmA, tmB, tmC, p, stream);
   return launch_gemm2<1, 0>(tmA, tmB, tmC, p, stream);
+}
+
+// Same contract as b200_gemm_bf16 (gemm.cu); requires M > 128 to be worthwhile.  Called by the dispatcher there.
+extern "C" int b200_gemm_bf16_2sm(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
+                                  int a_mn, int b_mn, int accumulate, cudaStream_t stream) {
+  return gemm2_run(A, B, C, M, N, K, lda, ldb, ldc, a_mn, b_mn, accumulate, nullptr, 0, 0, stream);
+}
+
+// GEMM whose epilogue is the first half of a reduce-scatter: D = A B^T as b200_gemm_bf16, but row block r of the output
+// (rows [r * M / world, (r + 1) * M / world)) is TMA-stored straight into dest_ptrs[r] -- a [M / world, N] bf16 buffer with
+// leading dimension ldc, for r != rank a slot in rank r's peer-mapped memory, so the partial sums cross NVLink tile by tile
+// while the tensor cores work on the following tiles (own block last).  The caller then barriers and sums its `world` slots
+// (b200_pull_reduce_bf16 on local memory).  dest_ptrs: HOST array; M / world must be a multiple of 256.
+extern "C" int b200_gemm_bf16_scatter(const void* A, const void* B, void* const* dest_ptrs, int world, int rank, int M, int N,
+                                      int K, int lda, int ldb, int ldc, int a_mn, int b_mn, cudaStream_t stream) {
+  using namespace b200;
+  B200_REQUIRE(world >= 1 && world <= 16 && rank >= 0 && rank < world, "gemm_scatter: bad world=%d rank=%d", world, rank);
+  B200_REQUIRE(M > 0 && M % world == 0 && (M / world) % G2_BM == 0, "gemm_scatter: M=%d / world=%d must be a multiple of %d rows",
+               M, world, G2_BM);
+  const int rows = M / world;
+  // tensor maps of the destination buffers live in device memory; they only depend on (pointers, shape), which repeat
+  // every other call (double-buffered slots), so they are built and uploaded once per distinct destination set
+  struct Entry {
+    void* ptr[16];
+    int world, rows, N, ldc;
+    CUtensorMap* dev;
+  };
+  static Entry cache[32];
+  static int n_cache = 0;
+  const CUtensorMap* dev_maps = nullptr;
+  for (int i = 0; i < n_cache && !dev_maps; ++i) {
+    const Entry& e = cache[i];
+    bool same = e.world == world && e.rows == rows && e.N == N && e.ldc == ldc;
+    for (int r = 0; same && r < world; ++r) same = e.ptr[r] == dest_ptrs[r];
+    if (same) dev_maps = e.dev;
+  }
+  if (!dev_maps) {
+    B200_REQUIRE(n_cache < 32, "gemm_scatter: more than 32 distinct destination sets");
+    Entry& e = cache[n_cache];
+    CUtensorMap host_maps[16];
+    for (int r = 0; r < world; ++r) {
+      B200_REQUIRE(dest_ptrs[r] != nullptr && (reinterpret_cast<uintptr_t>(dest_ptrs[r]) & 15) == 0 && ldc % 8 == 0,
+                   "gemm_scatter: destination %d must be 16B aligned, ldc %% 8 == 0", r);
+      const int rc = make_tmap_2d_bf16(&host_maps[r], dest_ptrs[r], rows, N, ldc, 64, 32);
+      if (rc) return rc;
+      e.ptr[r] = dest_ptrs[r];
+    }
+    e.world = world, e.rows = rows, e.N = N, e.ldc = ldc;
+    B200_CHECK_CUDA(cudaMalloc(reinterpret_cast<void**>(&e.dev), sizeof(CUtensorMap) * 16));
+    B200_CHECK_CUDA(cudaMemcpy(e.dev, host_maps, sizeof(CUtensorMap) * world, cudaMemcpyHostToDevice));
+    dev_maps = e.dev;
+    ++n_cache;
+  }
+  const int m_rot = ((rank + 1) % world) * (rows / G2_BM);
+  // C is only used for the (unused) plain output tensor map: point it at the own block
+  return gemm2_run(A, B, dest_ptrs[rank], M, N, K, lda, ldb, ldc, a_mn, b_mn, 0, dev_maps, rows, m_rot, stream);
 }

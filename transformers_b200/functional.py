@@ -41,6 +41,25 @@ def _peer_reduce_scatter(part, st):
     return ops.pull_reduce(st.peer.partial_ptrs(), st.rank * rows * C, rows * C, out)
 
 
+def _peer_gemm_reduce_scatter(x2, w, st, b_mn=False):
+    """Rowwise GEMM + reduce-scatter over peer memory.  With the scatter epilogue the GEMM itself delivers every finished
+    tile to its owner over NVLink (one kernel for the GEMM and the transfer) and the reduction reads local slots; otherwise
+    the partial stays local and the owners pull it.  Returns this rank's [T/N, C] rows of the summed result."""
+    ws = st.peer
+    T = x2.shape[0]
+    C = w.shape[1] if b_mn else w.shape[0]
+    rows = T // st.world
+    if ws.scatter_epilogue and rows % 256 == 0:
+        dest, mine = ws.next_staging(rows, C)
+        ops.gemm_scatter(x2, w, dest, st.rank, b_mn=b_mn)
+        ws.publish_partial()
+        out = torch.empty(rows, C, device=x2.device, dtype=x2.dtype)
+        return ops.pull_reduce(mine, 0, rows * C, out)
+    part = ws.next_partial(T, C)
+    ops.gemm(x2, w, b_mn=b_mn, out=part)
+    return _peer_reduce_scatter(part, st)
+
+
 def _peer_all_gather(local2, st):
     """All-gather of token shards over peer memory: publish the shard, barrier, then copy every peer's shard out with the
     copy engines on a side stream (no SM time); the own rows are a local copy.  Returns [T, K]."""
@@ -81,9 +100,7 @@ def _sp_dgrad_scatter(dy2, w, st):
 
     T = dy2.shape[0]
     if st.peer is not None:
-        part = st.peer.next_partial(T, w.shape[1])
-        ops.gemm(dy2, w, b_mn=True, out=part)
-        return _peer_reduce_scatter(part, st), [], None
+        return _peer_gemm_reduce_scatter(dy2, w, st, b_mn=True), [], None
     dx_local = dy2.new_empty(T // st.world, w.shape[1])
     works, keep = [], []
     for c, rows in enumerate(st.chunk_rows(T)):
@@ -100,9 +117,7 @@ def _sp_gemm_scatter(x2, w, st):
 
     T = x2.shape[0]
     if st.peer is not None:
-        part = st.peer.next_partial(T, w.shape[0])
-        ops.gemm(x2, w, out=part)
-        return _peer_reduce_scatter(part, st)
+        return _peer_gemm_reduce_scatter(x2, w, st)
     y_local = x2.new_empty(T // st.world, w.shape[0])
     works, keep = [], []
     for c, rows in enumerate(st.chunk_rows(T)):

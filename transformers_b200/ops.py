@@ -475,6 +475,22 @@ def grad_scale_(table: torch.Tensor, chunk_map: torch.Tensor, coef: torch.Tensor
 
 
 # ---------------------------------------------------------------------------------------------------- peer memory
+def gemm_scatter(a: torch.Tensor, b: torch.Tensor, dest_ptrs: list[int], rank: int, *, a_mn: bool = False,
+                 b_mn: bool = False) -> None:
+    """GEMM whose epilogue stores row block r of the [M, N] result into ``dest_ptrs[r]`` ([M / world, N] bf16, contiguous:
+    slots of peer-mapped buffers) -- the first half of a reduce-scatter fused into the GEMM (csrc/gemm2.cu SCATTER mode)."""
+    lib = _lib_ready()
+    _chk_bf16(a, b)
+    M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
+    N, Kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
+    if K != Kb or a.stride(1) != 1 or b.stride(1) != 1:
+        raise B200Error("gemm_scatter: operands must be 2-D with unit inner stride and matching contraction")
+    arr = (ctypes.c_void_p * len(dest_ptrs))(*dest_ptrs)
+    check(lib.b200_gemm_bf16_scatter(a.data_ptr(), b.data_ptr(), ctypes.cast(arr, ctypes.c_void_p), len(dest_ptrs), int(rank),
+                                     M, N, K, a.stride(0), b.stride(0), N, int(a_mn), int(b_mn), _stream()),
+          "b200_gemm_bf16_scatter")
+
+
 def pull_reduce(peer_ptrs: list[int], offset_elems: int, n_elems: int, out: torch.Tensor,
                 residual: torch.Tensor | None = None) -> torch.Tensor:
     """out[i] = bf16(residual[i] + sum_s peer_s[offset + i]) where peer_ptrs are the base addresses of every rank's

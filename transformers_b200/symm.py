@@ -22,7 +22,10 @@ import torch.distributed as dist
 
 
 class PeerWorkspace:
-    def __init__(self, group, device: torch.device | None = None):
+    def __init__(self, group, device: torch.device | None = None, scatter_epilogue: bool = False):
+        # scatter_epilogue: the rowwise GEMM stores every finished tile straight into the owner rank's slot (SCATTER mode of
+        # the CTA-pair GEMM) and the reduction reads local memory only; otherwise the GEMM writes locally and peers pull
+        self.scatter_epilogue = scatter_epilogue
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
@@ -60,6 +63,17 @@ class PeerWorkspace:
         self._j_partial += 1
         t, _ = self._partial[self._j_partial % 2]
         return t[: rows * cols].view(rows, cols)
+
+    def next_staging(self, rows: int, cols: int):
+        """Scatter-epilogue layout of the same buffer: ``world`` slots of [rows, cols]; slot s of rank r receives the partial
+        sums rank s computed for r's rows.  Returns (where this rank's GEMM stores block r for every r, this rank's slots)."""
+        self.reserve(rows * cols * self.world)
+        self._j_partial += 1
+        _, hdl = self._partial[self._j_partial % 2]
+        slot_bytes = rows * cols * 2
+        dest = [int(hdl.buffer_ptrs[r]) + self.rank * slot_bytes for r in range(self.world)]
+        mine = [int(hdl.buffer_ptrs[self.rank]) + s * slot_bytes for s in range(self.world)]
+        return dest, mine
 
     def publish_partial(self) -> None:
         """Device-side barrier on the current stream: everything written into the current partial buffer before this
