@@ -62,4 +62,8 @@ T=300 run env B200_GEMM2_SYNC=1 ncu --metrics gpu__time_duration.sum,dram__bytes
   --clock-control none -k regex:gemm_bf16 --csv --log-file gpurun_out/gemm_traffic_sync.csv python tests/cuda/prof_kernels.py gemm
 T=300 run env B200_GEMM2_SYNC=1 python bench.py --steps 3 --warmup 3 --layers 8 --no-cpu-baseline
 T=300 run python bench.py --steps 3 --warmup 3 --layers 8 --no-cpu-baseline
+# 8. the other BASELINE configs, measured (JSON lines): Mixtral-8x7B forward (configs[3]), Gemma-2-9B generate (configs[4])
+T=600 run python tests/cuda/bench_configs45.py mixtral
+T=600 run python tests/cuda/bench_configs45.py gemma2
+T=600 run env B200_GEMV=1 B200_DECODE_ATTN=1 python tests/cuda/bench_configs45.py gemma2 --inplace-sliding
 fi
