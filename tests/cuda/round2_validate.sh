@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # First GPU call of the next round: validates everything that was written after round 1's GPU budget was spent
 # (never run on a device), cheapest first.  Two parts, because a multi-GPU box is charged N x its time:
-#   gpurun --timeout 1500 -- 'PART=single bash tests/cuda/round2_validate.sh 2>&1 | tee gpurun_out/round2_single.log'
+#   gpurun --timeout 2700 -- 'PART=single bash tests/cuda/round2_validate.sh 2>&1 | tee gpurun_out/round2_single.log'
 #   gpurun --gpus 2 --timeout 900 -- 'PART=multi bash tests/cuda/round2_validate.sh 2>&1 | tee gpurun_out/round2_multi.log'
 # Every step is bounded by `timeout`; a failing step is reported and the script goes on.
 set -u
