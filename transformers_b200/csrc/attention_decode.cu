@@ -14,7 +14,9 @@
 //   kernel 2 (grid Hq x B): merges the nsplit partials, writes bf16 out and the natural-log lse.
 //
 // Algorithmic bytes: B * Hkv * ctx * D * 4 (K and V once) + workspace 2 * B * Hq * nsplit * (D + 2) * 4.
+#ifndef B200_HOST_EMU
 #include "attn_common.cuh"
+#endif
 
 namespace b200 {
 
@@ -174,6 +176,7 @@ __global__ void decode_attn_combine_kernel(DecodeParams p) {
     p.lse[(static_cast<int64_t>(b) * p.Hq + hq) * p.lse_stride] = ll > 0.f ? mm * 0.6931471805599453f + logf(ll) : -INFINITY;
 }
 
+#ifndef B200_HOST_EMU
 template <int D, int G>
 static int launch_decode(const DecodeParams& p, cudaStream_t stream) {
   decode_attn_split_kernel<D, G><<<dim3(p.nsplit, p.Hkv, p.B), DEC_WARPS * 32, 0, stream>>>(p);
@@ -196,6 +199,8 @@ static int dispatch_g(const DecodeParams& p, int G, cudaStream_t stream) {
   }
 }
 
+#endif  // B200_HOST_EMU
+
 }  // namespace b200
 
 // number of context splits b200_attn_decode will use (workspace = B * Hq * nsplit * (D + 2) floats)
@@ -211,6 +216,7 @@ extern "C" int b200_attn_decode_splits(int B, int Hkv, int Skv) {
   return n;
 }
 
+#ifndef B200_HOST_EMU
 // q [B, 1, Hq, D] (q_bs, q_hs strides), k / v [B, Skv, Hkv, D] strided (batch, row, head), out [B, 1, Hq, D]; lse optional.
 extern "C" int b200_attn_decode(const void* q, const void* k, const void* v, void* out, float* lse, int lse_stride,
                                 float* workspace, int B, int Skv, int Hq, int Hkv, int D, int64_t q_bs, int64_t q_hs,
@@ -249,3 +255,4 @@ extern "C" int b200_attn_decode(const void* q, const void* k, const void* v, voi
   if (D == 128) return dispatch_g<128>(p, G, stream);
   return dispatch_g<64>(p, G, stream);
 }
+#endif  // B200_HOST_EMU

@@ -9,7 +9,9 @@
 // read through the read-only path) and the warp reduces with shuffles.  Algorithmic bytes: N*K*2 (+ M*K*2 + M*N*2).
 #include <cuda_bf16.h>
 
+#ifndef B200_HOST_EMU
 #include "common.cuh"
+#endif
 
 namespace b200 {
 
@@ -74,6 +76,7 @@ gemv_bf16_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __res
   }
 }
 
+#ifndef B200_HOST_EMU
 template <int M>
 static int launch_gemv(const void* x, const void* W, void* y, int N, int K, int ldx, int ldw, int ldy, cudaStream_t stream) {
   gemv_bf16_kernel<M><<<(N + GEMV_WARPS - 1) / GEMV_WARPS, GEMV_WARPS * 32, 0, stream>>>(
@@ -83,8 +86,11 @@ static int launch_gemv(const void* x, const void* W, void* y, int N, int K, int 
   return B200_OK;
 }
 
+#endif  // B200_HOST_EMU
+
 }  // namespace b200
 
+#ifndef B200_HOST_EMU
 using namespace b200;
 
 // y[M, N] = x[M, K] W[N, K]^T, 1 <= M <= 4, both operands K-major (x row stride ldx, W row stride ldw, elements).
@@ -102,3 +108,4 @@ extern "C" int b200_gemv_bf16(const void* x, const void* W, void* y, int M, int 
     default: return launch_gemv<4>(x, W, y, N, K, ldx, ldw, ldy, stream);
   }
 }
+#endif  // B200_HOST_EMU

@@ -15,7 +15,9 @@
 // moments (read p,g,m,v + write p,m,v), 22 B with fp32 moments; norm 2 B; scale 4 B.
 #include <cuda_bf16.h>
 
+#ifndef B200_HOST_EMU  // tests/emu/cuda_emu.h provides the macros when the kernels are run on the host
 #include "common.cuh"
+#endif
 
 namespace b200 {
 
@@ -30,9 +32,13 @@ struct AdamArgs {
 // IEEE sqrt + two IEEE divisions per element would make this 14 B/element stream ALU-bound (measured on the GLU kernels,
 // profiles/README.md)
 __device__ __forceinline__ float sqrt_approx(float x) {
+#ifdef B200_HOST_EMU
+  return sqrtf(x);
+#else
   float y;
   asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#endif
 }
 
 __device__ __forceinline__ void adamw_update(float& p, float g, float& m, float& v, const AdamArgs& a) {
@@ -212,6 +218,7 @@ grad_scale_kernel(const int64_t* __restrict__ table, const int2* __restrict__ ch
 
 }  // namespace b200
 
+#ifndef B200_HOST_EMU
 using namespace b200;
 
 extern "C" int b200_optim_chunk_elems(void) { return OPT_CHUNK; }
@@ -254,3 +261,4 @@ extern "C" int b200_grad_scale(const int64_t* tensor_table, const int32_t* chunk
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }
+#endif  // B200_HOST_EMU

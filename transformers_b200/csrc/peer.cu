@@ -11,7 +11,9 @@
 // Algorithmic bytes per output element: 2 B x world (one local + world-1 remote reads) + 2 B residual + 2 B write.
 #include <cuda_bf16.h>
 
+#ifndef B200_HOST_EMU
 #include "common.cuh"
+#endif
 
 namespace b200 {
 
@@ -64,6 +66,7 @@ __global__ void __launch_bounds__(256) pull_reduce_kernel(PeerPtrs src, int64_t 
   }
 }
 
+#ifndef B200_HOST_EMU
 template <int WORLD>
 static int launch_pull_reduce(const PeerPtrs& src, int64_t offset, int64_t n8, const void* residual, void* out,
                               cudaStream_t stream) {
@@ -76,8 +79,11 @@ static int launch_pull_reduce(const PeerPtrs& src, int64_t offset, int64_t n8, c
   return B200_OK;
 }
 
+#endif  // B200_HOST_EMU
+
 }  // namespace b200
 
+#ifndef B200_HOST_EMU
 using namespace b200;
 
 // peer_ptrs: HOST array of `world` device pointers (this rank's own buffer included, in rank order), each the base of that
@@ -107,3 +113,4 @@ extern "C" int b200_pull_reduce_bf16(const void* const* peer_ptrs, int world, in
       return B200_ERR_INVALID;
   }
 }
+#endif  // B200_HOST_EMU
