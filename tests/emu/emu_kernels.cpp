@@ -7,6 +7,7 @@
 #include "peer.cu"
 #include "gemv.cu"
 #include "attention_decode.cu"
+#include "ce_sharded.cu"
 
 using namespace b200;
 
@@ -92,4 +93,13 @@ extern "C" int emu_attn_decode(const void* q, const void* k, const void* v, void
   CASE(256, 4) CASE(256, 8)
 #undef CASE
   return -22;
+}
+
+extern "C" int emu_ce_bwd_sharded(const void* logits, const int64_t* target_local, const float* lse, const float* row_scale,
+                                  void* dlogits, int T, int V, int ld, int ld_out) {
+  emu::launch(dim3(T), dim3(1024), [&] {
+    ce_bwd_sharded_kernel(reinterpret_cast<const __nv_bfloat16*>(logits), target_local, lse, row_scale,
+                          reinterpret_cast<__nv_bfloat16*>(dlogits), V, ld, ld_out);
+  });
+  return 0;
 }

@@ -1,4 +1,4 @@
-"""The CUDA-core kernels that were written without a GPU (optim.cu, peer.cu, gemv.cu, attention_decode.cu), executed on the
+"""The CUDA-core kernels that were written without a GPU (optim.cu, peer.cu, gemv.cu, attention_decode.cu, ce_sharded.cu), executed on the
 HOST by tests/emu (one std::thread per CUDA thread, real warp-shuffle and barrier semantics): the kernels' own source is
 compiled with g++ and checked against torch.  This pins indexing, vector/tail paths, shuffle reductions and shared-memory
 merges before the first device run; device-only aspects (coalescing, latency, the launchers) are left to
@@ -34,6 +34,7 @@ def emu(tmp_path_factory):
     lib.emu_grad_scale.argtypes = [p, p, i32, p]
     lib.emu_pull_reduce.argtypes = [p, i32, i64, i64, p, p, i32]
     lib.emu_gemv.argtypes = [p, p, p, i32, i32, i32, i32, i32, i32]
+    lib.emu_ce_bwd_sharded.argtypes = [p, p, p, p, p, i32, i32, i32, i32]
     lib.emu_attn_decode.argtypes = [p, p, p, p, p, i32, p, i32, i32, i32, i32, i32] + [i64] * 10 + [f32, f32, i32, p, p, i32]
     return lib
 
@@ -155,3 +156,25 @@ def test_decode_attention_kernels_emulated(emu, B, Hq, Hkv, D, ctx, window, soft
     want = torch.einsum("bhk,bkhd->bhd", torch.softmax(s, -1), v)
     torch.testing.assert_close(out[:, 0].float(), want, atol=1e-2, rtol=1e-2)
     torch.testing.assert_close(lse[..., 0], torch.logsumexp(s, -1), atol=1e-3, rtol=1e-3)
+
+
+@pytest.mark.timeout(300)
+def test_ce_bwd_sharded_kernel_emulated(emu):
+    """Two vocabulary shards: the sharded gradient kernel with the GLOBAL lse must reproduce the full softmax - one-hot."""
+    torch.manual_seed(5)
+    T, V, N = 3, 8 * 1030 + 4, 2  # per shard: > 1024 vectors (second loop trip for some threads) plus a scalar tail
+    Vl = V // N
+    logits = (torch.randn(T, V) * 2).to(BF)
+    tgt = torch.tensor([5, V - 2, Vl + 1])
+    row_scale = torch.tensor([0.25, 0.0, 0.5])
+    lse = torch.logsumexp(logits.float(), -1)
+    want = torch.softmax(logits.float(), -1)
+    want[torch.arange(T), tgt] -= 1.0
+    want = want * row_scale[:, None]
+    for r in range(N):
+        shard = logits[:, r * Vl:(r + 1) * Vl].contiguous()
+        local = tgt - r * Vl
+        local = torch.where((local >= 0) & (local < Vl), local, torch.full_like(local, -1))
+        out = torch.full((T, Vl), float("nan"), dtype=BF)
+        emu.emu_ce_bwd_sharded(shard.data_ptr(), local.data_ptr(), lse.data_ptr(), row_scale.data_ptr(), out.data_ptr(), T, Vl, Vl, Vl)
+        torch.testing.assert_close(out.float(), want[:, r * Vl:(r + 1) * Vl], atol=2e-6, rtol=8e-3)
