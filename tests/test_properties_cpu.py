@@ -91,3 +91,43 @@ def test_packed_detection_only_accepts_adjacent_row_views(sizes, K, shift):
     assert not _is_packed(buf, [v.clone() for v in views])
     if shift and len(views) > 1 and sizes[0] != sizes[1]:
         assert not _is_packed(buf, [views[1], views[0]] + views[2:])  # same rows, wrong order
+
+
+@settings(max_examples=60, deadline=None)
+@given(world=st.sampled_from([1, 2, 4, 8]), blocks=st.integers(1, 3), num_n=st.integers(1, 9), group_m=st.sampled_from([1, 4, 8, 16]),
+       rank=st.integers(0, 7))
+def test_scatter_tile_order_visits_every_tile_once_and_own_block_last(world, blocks, num_n, group_m, rank):
+    """Restatement of the tile walk of gemm2.cu's SCATTER mode (tile_coords + m_rot rotation, owner = row0 / rows_per_owner):
+    every (m-tile, n-tile) is produced exactly once, the destination strip index stays inside the owner's buffer, and the
+    rotation makes the own row block the LAST one in tile order (so remote blocks travel while later tiles compute)."""
+    rank %= world
+    tiles_per_owner = blocks                      # rows_per_owner = blocks * 256
+    num_m = world * tiles_per_owner
+    rows_per_owner = tiles_per_owner * 256
+    m_rot = ((rank + 1) % world) * tiles_per_owner
+    seen, owners_in_order = set(), []
+    for tile in range(num_m * num_n):
+        group_size = group_m * num_n
+        group = tile // group_size
+        first_m = group * group_m
+        gsz = min(group_m, num_m - first_m)
+        in_group = tile - group * group_size
+        tm = first_m + in_group % gsz
+        tn = in_group // gsz
+        tm += m_rot
+        if tm >= num_m:
+            tm -= num_m
+        assert 0 <= tm < num_m and 0 <= tn < num_n and (tm, tn) not in seen
+        seen.add((tm, tn))
+        for cta_rank in range(2):
+            for q in range(4):
+                row0 = tm * 256 + cta_rank * 128 + q * 32
+                owner = row0 // rows_per_owner
+                local = row0 - owner * rows_per_owner
+                assert 0 <= owner < world and 0 <= local and local + 32 <= rows_per_owner
+        owners_in_order.append(tm * 256 // rows_per_owner)
+    assert len(seen) == num_m * num_n
+    if world > 1 and group_m <= tiles_per_owner * world:
+        first_own = owners_in_order.index(rank)
+        assert all(o == rank for o in owners_in_order[first_own:]) or group_m > 1  # strict "own block last" holds for group_m == 1
+        assert owners_in_order[-1] == rank or group_m > 1
