@@ -94,7 +94,40 @@ template <typename T>
 inline T __ldg(const T* p) {
   return *p;
 }
+template <typename T>
+inline T __ldcs(const T* p) {
+  return *p;
+}
+template <typename T>
+inline void __stcs(T* p, T v) {
+  *p = v;
+}
 inline int min(int a, int b) { return a < b ? a : b; }
+inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
+inline float __frcp_rn(float x) { return 1.0f / x; }
+#include <mutex>
+namespace emu {
+inline std::mutex g_atomic_mutex;
+}
+inline int atomicExch(int* p, int v) {
+  std::lock_guard<std::mutex> g(emu::g_atomic_mutex);
+  const int old = *p;
+  *p = v;
+  return old;
+}
+inline int atomicAdd(int* p, int v) {
+  std::lock_guard<std::mutex> g(emu::g_atomic_mutex);
+  const int old = *p;
+  *p = old + v;
+  return old;
+}
+inline __nv_bfloat162 atomicAdd(__nv_bfloat162* p, __nv_bfloat162 v) {
+  std::lock_guard<std::mutex> g(emu::g_atomic_mutex);
+  const __nv_bfloat162 old = *p;
+  const float2 a = __bfloat1622float2(old), b = __bfloat1622float2(v);
+  *p = __floats2bfloat162_rn(a.x + b.x, a.y + b.y);
+  return old;
+}
 inline float __fdividef(float a, float b) { return a / b; }
 inline float __expf(float x) { return std::exp(x); }
 

@@ -8,6 +8,9 @@
 #include "gemv.cu"
 #include "attention_decode.cu"
 #include "ce_sharded.cu"
+#include "elementwise.cu"
+#include "kvcache.cu"
+#include "moe.cu"
 
 using namespace b200;
 
@@ -100,6 +103,124 @@ extern "C" int emu_ce_bwd_sharded(const void* logits, const int64_t* target_loca
   emu::launch(dim3(T), dim3(1024), [&] {
     ce_bwd_sharded_kernel(reinterpret_cast<const __nv_bfloat16*>(logits), target_local, lse, row_scale,
                           reinterpret_cast<__nv_bfloat16*>(dlogits), V, ld, ld_out);
+  });
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// The GPU-validated CUDA-core kernels (elementwise.cu, kvcache.cu, moe.cu) with the launch configurations of their C-ABI
+// launchers restated here (the launchers themselves contain <<<>>> and stay device-only).
+static inline int cdiv(size_t a, size_t b) { return static_cast<int>((a + b - 1) / b); }
+using bf = __nv_bfloat16;
+
+extern "C" int emu_embedding_fwd(const int64_t* ids, const void* w, void* out, int T, int H, int V, float scale, int has_scale, int* err) {
+  emu::launch(dim3(cdiv(T, 8)), dim3(256), [&] {
+    embedding_fwd_kernel(ids, reinterpret_cast<const uint4*>(w), reinterpret_cast<uint4*>(out), T, H / 8, V, scale, has_scale, err);
+  });
+  return 0;
+}
+extern "C" int emu_embedding_bwd(const int64_t* ids, const void* dout, void* dw, int T, int H, int V, int64_t pad, float scale, int has_scale) {
+  emu::launch(dim3(cdiv(T, 8)), dim3(256), [&] {
+    embedding_bwd_kernel(ids, reinterpret_cast<const __nv_bfloat162*>(dout), reinterpret_cast<__nv_bfloat162*>(dw), T, H / 2, V, pad, scale, has_scale);
+  });
+  return 0;
+}
+extern "C" int emu_rmsnorm_fwd(const void* x, const void* res_in, const void* w, void* res_out, void* y, float* rstd, int T, int H, float eps, int gemma) {
+  const uint4 *xp = reinterpret_cast<const uint4*>(x), *rp = reinterpret_cast<const uint4*>(res_in), *wp = reinterpret_cast<const uint4*>(w);
+  uint4 *rop = reinterpret_cast<uint4*>(res_out), *yp = reinterpret_cast<uint4*>(y);
+  const dim3 grid(cdiv(T, 4)), block(128);
+#define NL(G, A, N) emu::launch(grid, block, [&] { rmsnorm_fwd_kernel<G, A, N>(xp, rp, wp, rop, yp, rstd, T, H / 8, eps); })
+#define ND(N) do { if (res_in) { if (gemma) NL(true, true, N); else NL(false, true, N); } else { if (gemma) NL(true, false, N); else NL(false, false, N); } } while (0)
+  if (H <= 2048) ND(8); else if (H <= 4096) ND(16); else ND(32);
+#undef ND
+#undef NL
+  return 0;
+}
+extern "C" int emu_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx, void* dw, float* ws, int T, int H, int gemma, int acc) {
+  const int threads = ((H / 8 + 31) / 32) * 32;
+  int grid = 2 * 148;
+  if (grid > T) grid = T;
+  const uint4 *dyp = reinterpret_cast<const uint4*>(dy), *xp = reinterpret_cast<const uint4*>(x), *wp = reinterpret_cast<const uint4*>(w);
+  uint4* dxp = reinterpret_cast<uint4*>(dx);
+  if (threads <= 512) {
+    if (gemma) emu::launch(dim3(grid), dim3(threads), [&] { rmsnorm_bwd_kernel<true, 1, 512>(dyp, xp, wp, rstd, dxp, ws, T, H / 8); });
+    else emu::launch(dim3(grid), dim3(threads), [&] { rmsnorm_bwd_kernel<false, 1, 512>(dyp, xp, wp, rstd, dxp, ws, T, H / 8); });
+  } else {
+    if (gemma) emu::launch(dim3(grid), dim3(threads), [&] { rmsnorm_bwd_kernel<true, 1, 1024>(dyp, xp, wp, rstd, dxp, ws, T, H / 8); });
+    else emu::launch(dim3(grid), dim3(threads), [&] { rmsnorm_bwd_kernel<false, 1, 1024>(dyp, xp, wp, rstd, dxp, ws, T, H / 8); });
+  }
+  emu::launch(dim3(cdiv(H, 256)), dim3(256), [&] { reduce_partials_kernel(ws, reinterpret_cast<bf*>(dw), grid, H, acc); });
+  return 0;
+}
+extern "C" int emu_rope(void* qkv, const void* c, const void* s, int B, int S, int n_rot, int D, int row_stride, int cos_batch, int bwd) {
+  const int T = B * S, cbs = cos_batch == 1 ? 0 : S * D;
+  int threads = n_rot * (D / 16);
+  threads = threads > 512 ? 512 : ((threads + 31) / 32) * 32;
+  auto *q = reinterpret_cast<bf*>(qkv);
+  auto *cp = reinterpret_cast<const bf*>(c), *sp = reinterpret_cast<const bf*>(s);
+  if (bwd) emu::launch(dim3(T), dim3(threads), [&] { rope_kernel<true>(q, cp, sp, T, S, n_rot, D, row_stride, cbs); });
+  else emu::launch(dim3(T), dim3(threads), [&] { rope_kernel<false>(q, cp, sp, T, S, n_rot, D, row_stride, cbs); });
+  return 0;
+}
+extern "C" int emu_glu_fwd(const void* g, const void* u, void* out, int T, int I, int ld_gu, int ld_out, int gelu) {
+  emu::launch(dim3(cdiv(I / 8, 256), cdiv(T, GLU_ROWS)), dim3(256), [&] {
+    glu_fwd_kernel(reinterpret_cast<const bf*>(g), reinterpret_cast<const bf*>(u), reinterpret_cast<bf*>(out), T, I / 8, ld_gu, ld_out, gelu);
+  });
+  return 0;
+}
+extern "C" int emu_glu_bwd(const void* dh, const void* g, const void* u, void* dg, void* du, int T, int I, int ld_dh, int ld_gu, int ld_dgu, int gelu) {
+  emu::launch(dim3(cdiv(I / 8, 256), cdiv(T, GLU_BWD_ROWS)), dim3(256), [&] {
+    glu_bwd_kernel(reinterpret_cast<const bf*>(dh), reinterpret_cast<const bf*>(g), reinterpret_cast<const bf*>(u), reinterpret_cast<bf*>(dg),
+                   reinterpret_cast<bf*>(du), T, I / 8, ld_dh, ld_gu, ld_dgu, gelu);
+  });
+  return 0;
+}
+extern "C" int emu_add(const void* a, const void* b, void* out, int64_t n) {
+  emu::launch(dim3(cdiv(n / 8, 256)), dim3(256), [&] {
+    add_kernel(reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b), reinterpret_cast<uint4*>(out), static_cast<size_t>(n / 8));
+  });
+  return 0;
+}
+extern "C" int emu_ce_fwd(const void* logits, const int64_t* labels, float* lse, float* rows, float* loss, float* denom, int B, int S, int V, int ld,
+                          int shift, int64_t ignore, float num_items) {
+  const int T = B * S;
+  emu::launch(dim3(T), dim3(1024), [&] { ce_fwd_kernel(reinterpret_cast<const bf*>(logits), labels, lse, rows, T, S, V, ld, shift, ignore); });
+  emu::launch(dim3(1), dim3(1024), [&] { ce_reduce_kernel(rows, labels, loss, denom, T, S, shift, ignore, num_items); });
+  return 0;
+}
+extern "C" int emu_ce_bwd(const void* logits, const int64_t* labels, const float* lse, const float* dloss, const float* denom, void* dl, int B, int S,
+                          int V, int ld, int ld_out, int shift, int64_t ignore) {
+  const int T = B * S;
+  emu::launch(dim3(T), dim3(1024), [&] {
+    ce_bwd_kernel(reinterpret_cast<const bf*>(logits), labels, lse, dloss, denom, reinterpret_cast<bf*>(dl), T, S, V, ld, ld_out, shift, ignore);
+  });
+  return 0;
+}
+extern "C" int emu_kv_append(const void* kn, const void* vn, void* kc, void* vc, int B, int H, int q, int D, int64_t ks_b, int64_t ks_h, int64_t ks_r,
+                             int64_t vs_b, int64_t vs_h, int64_t vs_r, int64_t cs_b, int64_t cs_h, int64_t cs_r, int offset) {
+  const int total = B * H * q;
+  emu::launch(dim3((total * 32 + 255) / 256), dim3(256), [&] {
+    kv_append_kernel(reinterpret_cast<const bf*>(kn), reinterpret_cast<const bf*>(vn), reinterpret_cast<bf*>(kc), reinterpret_cast<bf*>(vc), B, H, q,
+                     D / 8, ks_b, ks_h, ks_r, vs_b, vs_h, vs_r, cs_b, cs_h, cs_r, offset);
+  });
+  return 0;
+}
+extern "C" int emu_moe_route(const int64_t* idx, int* counts, int* offsets, int* cursor, int* slot, int* tok, int T, int topk, int E) {
+  const int n = T * topk;
+  int grid = (n + 255) / 256;
+  if (grid > 1024) grid = 1024;
+  emu::launch(dim3(grid), dim3(256), [&] { moe_count_kernel(idx, counts, n, E); });
+  emu::launch(dim3(1), dim3(32), [&] { moe_scan_kernel(counts, offsets, cursor, E); });
+  emu::launch(dim3((n + 255) / 256), dim3(256), [&] { moe_scatter_kernel(idx, offsets, cursor, slot, tok, n, topk, E); });
+  return 0;
+}
+extern "C" int emu_moe_gather(const void* x, const int* tok, void* xs, int n, int H) {
+  emu::launch(dim3((n * 32 + 255) / 256), dim3(256), [&] { moe_gather_kernel(reinterpret_cast<const uint4*>(x), tok, reinterpret_cast<uint4*>(xs), n, H / 8); });
+  return 0;
+}
+extern "C" int emu_moe_combine(const void* ys, const int* slot, const float* w, void* out, int T, int topk, int H) {
+  emu::launch(dim3((T * 32 + 255) / 256), dim3(256), [&] {
+    moe_combine_kernel(reinterpret_cast<const uint4*>(ys), slot, w, reinterpret_cast<uint4*>(out), T, topk, H / 8);
   });
   return 0;
 }

@@ -2,7 +2,9 @@
 // variants), RoPE fwd/bwd, SwiGLU / GeGLU fwd/bwd, residual add, causal-LM cross-entropy fwd/bwd.
 // All are streaming kernels: 16-byte vectorised coalesced accesses, fp32 math, bf16 I/O, one pass over HBM where the
 // algorithm allows.  Rounding points follow the reference eager path.
+#ifndef B200_HOST_EMU  // tests/emu executes the kernels below on the host (launchers and inline PTX excluded)
 #include "common.cuh"
+#endif
 
 #include <cuda_bf16.h>
 #include <math.h>
@@ -314,9 +316,13 @@ __global__ void rope_kernel(__nv_bfloat16* __restrict__ qkv, const __nv_bfloat16
 // first version used IEEE division and recomputed the exponential for the gradient, which made glu_bwd ALU-bound
 // (~50 instructions per element, 0.46 ms of pure issue per call at the Llama-3-8B shape).
 __device__ __forceinline__ float fast_tanhf(float x) {
+#ifdef B200_HOST_EMU
+  return tanhf(x);
+#else
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#endif
 }
 __device__ __forceinline__ void act_fwd_grad(float g, int gelu, float& act, float& dact) {
   if (!gelu) {
@@ -565,6 +571,7 @@ static inline int ceil_div(size_t a, size_t b) { return static_cast<int>((a + b 
 
 }  // namespace b200
 
+#ifndef B200_HOST_EMU
 using namespace b200;
 
 #define B200_ALIGNED16(p) ((reinterpret_cast<uintptr_t>(p) & 15) == 0)
@@ -737,3 +744,4 @@ extern "C" int b200_ce_bwd(const void* logits, const int64_t* labels, const floa
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }
+#endif  // B200_HOST_EMU

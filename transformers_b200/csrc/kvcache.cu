@@ -5,7 +5,9 @@
 // context).  Here the cache lives in a preallocated [B, Hkv, capacity, D] buffer and the new rows are
 // written at their position: algorithmic traffic 2 * Hkv * D * 2 B per token per layer (4 KB for Llama-3-8B).
 // One warp per (batch, head, new token) row; 16-byte vector copies; K and V in the same launch.
+#ifndef B200_HOST_EMU
 #include "common.cuh"
+#endif
 
 #include <cuda_bf16.h>
 
@@ -35,6 +37,7 @@ __global__ void kv_append_kernel(const __nv_bfloat16* __restrict__ k_new, const 
 
 }  // namespace b200
 
+#ifndef B200_HOST_EMU
 // k_new / v_new: [B, H, q_len, D] strided views (strides in elements: batch, head, row; unit inner stride);
 // k_cache / v_cache: [B, H, capacity, D] with the given (batch, head, row) strides; rows [offset, offset + q_len) are
 // written.  The caller guarantees offset + q_len <= capacity.
@@ -59,3 +62,4 @@ extern "C" int b200_kv_append(const void* k_new, const void* v_new, void* k_cach
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }
+#endif  // B200_HOST_EMU

@@ -9,14 +9,20 @@
 //   moe_gather  : x_sorted[slot, :] = x[t, :]                          (16 B vector copies, warp per row)
 //   moe_combine : out[t, :] = sum_k bf16(w[t,k] * y_sorted[slot[t,k], :])   (fp32 accumulate, bf16 out)
 // The expert GEMMs themselves are b200_gemm_bf16 launches on contiguous row ranges of x_sorted.
+#ifndef B200_HOST_EMU
 #include "common.cuh"
+#endif
 
 #include <cuda_bf16.h>
 
 namespace b200 {
 
 __global__ void moe_count_kernel(const int64_t* __restrict__ idx, int* __restrict__ counts, int n, int E) {
+#ifdef B200_HOST_EMU
+  static int sh[4096];  // dynamic shared memory of the launch (E ints)
+#else
   extern __shared__ int sh[];
+#endif
   for (int e = threadIdx.x; e < E; e += blockDim.x) sh[e] = 0;
   __syncthreads();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -95,6 +101,7 @@ __global__ void moe_combine_kernel(const uint4* __restrict__ ys, const int* __re
 
 }  // namespace b200
 
+#ifndef B200_HOST_EMU
 using namespace b200;
 
 // top_k_index int64 [T, topk] -> counts[E] (zeroed by the caller), offsets[E+1], cursor[E] (scratch), slot[T*topk],
@@ -134,3 +141,4 @@ extern "C" int b200_moe_combine(const void* y_sorted, const int* slot, const flo
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }
+#endif  // B200_HOST_EMU
