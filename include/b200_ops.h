@@ -127,12 +127,14 @@ int b200_attn_decode(const void* q, const void* k, const void* v, void* out, flo
 /* ---- optimizer step after the path ---------------------------------------------------------------
  * Trainer clips the global gradient norm (trainer.py:1783-1785, _clip_grad_norm :2538-2542 -> torch.nn.utils.clip_grad_norm_)
  * and calls optimizer.step() (:1788) on torch.optim.AdamW (trainer_optimizer.py:201-208).  Multi-tensor, one launch per
- * param group.  tensor_table: device int64 [n_tensors][6] = {param*, grad*, exp_avg*, exp_avg_sq*, numel, 0} (bf16 params
+ * param group.  tensor_table: device int64 [n_tensors][6] = {param*, grad*, exp_avg*, exp_avg_sq*, numel, fp32 master* or 0} (bf16 params
  * and grads; moments bf16 or fp32); chunk_map: device int32 [n_chunks][2] = {tensor index, chunk index} with chunks of
  * b200_optim_chunk_elems() elements. */
 int b200_optim_chunk_elems(void);
 /* torch.optim.AdamW update with step_size = lr / bias_correction1, denom = sqrt(v) / bias_correction2_sqrt + eps; every
- * gradient is multiplied by *grad_scale first when grad_scale != NULL (fused clipping: pass out2 + 1 of b200_grad_norm). */
+ * gradient is multiplied by *grad_scale first when grad_scale != NULL (fused clipping: pass out2 + 1 of b200_grad_norm).
+ * state_is_fp32: bit 0 = fp32 moments (else bf16); bit 1 = the table's sixth column points to fp32 master parameters: the
+ * update runs on them and the bf16 parameter becomes their rounding. */
 int b200_adamw_step(const int64_t* tensor_table, const int32_t* chunk_map, int n_chunks, int state_is_fp32, float lr,
                     float beta1, float beta2, float eps, float weight_decay, float bias_correction1,
                     float bias_correction2_sqrt, const float* grad_scale, b200_stream_t stream);

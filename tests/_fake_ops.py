@@ -294,22 +294,25 @@ def _rows(table):
     return [tuple(int(x) for x in r) for r in table.tolist()]
 
 
-def adamw_step(table, chunk_map, *, state_fp32, lr, beta1, beta2, eps, weight_decay, bias_correction1, bias_correction2_sqrt,
-               grad_scale=None):
+def adamw_step(table, chunk_map, *, state_fp32, master=False, lr, beta1, beta2, eps, weight_decay, bias_correction1,
+               bias_correction2_sqrt, grad_scale=None):
     chunk = optim_chunk_elems()
     seen = {}
     for ti, ci in chunk_map.tolist():
         seen.setdefault(ti, []).append(ci)
     gs = float(grad_scale[0]) if grad_scale is not None else 1.0
-    for ti, (pp, gp, mp, vp, n, _) in enumerate(_rows(table)):
+    for ti, (pp, gp, mp, vp, n, mw) in enumerate(_rows(table)):
         assert seen.get(ti) == list(range((n + chunk - 1) // chunk)), "chunk map must cover every tensor exactly once"
         p, g, m, v = _PTRS[pp], _PTRS[gp], _PTRS[mp], _PTRS[vp]
         assert p.numel() == n and (m.dtype == torch.float32) == bool(state_fp32)
-        pf, gf, mf, vf = p.float(), g.float() * gs, m.float(), v.float()
+        assert bool(mw) == bool(master)
+        pf, gf, mf, vf = (_PTRS[mw].float() if master else p.float()), g.float() * gs, m.float(), v.float()
         pf = pf - lr * weight_decay * pf
         mf = mf + (gf - mf) * (1.0 - beta1)
         vf = beta2 * vf + (1.0 - beta2) * gf * gf
         pf = pf - (lr / bias_correction1) * (mf / (vf.sqrt() / bias_correction2_sqrt + eps))
+        if master:
+            _PTRS[mw].copy_(pf)
         p.copy_(pf)
         m.copy_(mf)
         v.copy_(vf)

@@ -18,10 +18,13 @@ extern "C" int emu_adamw(const int64_t* table, const int32_t* chunks, int n_chun
                          float beta2, float eps, float wd, float bc1, float bc2_sqrt, const float* grad_scale) {
   AdamArgs a{lr, beta1, beta2, eps, wd, lr / bc1, 1.f / bc2_sqrt};
   const int2* ch = reinterpret_cast<const int2*>(chunks);
-  if (state_fp32)
-    emu::launch(dim3(n_chunks), dim3(OPT_THREADS), [&] { adamw_multi_kernel<float>(table, ch, a, grad_scale); });
-  else
-    emu::launch(dim3(n_chunks), dim3(OPT_THREADS), [&] { adamw_multi_kernel<__nv_bfloat16>(table, ch, a, grad_scale); });
+  const dim3 g(n_chunks), b(OPT_THREADS);
+  switch (state_fp32 & 3) {  // bit 0: fp32 moments, bit 1: fp32 master parameters (like b200_adamw_step)
+    case 0: emu::launch(g, b, [&] { adamw_multi_kernel<__nv_bfloat16, false>(table, ch, a, grad_scale); }); break;
+    case 1: emu::launch(g, b, [&] { adamw_multi_kernel<float, false>(table, ch, a, grad_scale); }); break;
+    case 2: emu::launch(g, b, [&] { adamw_multi_kernel<__nv_bfloat16, true>(table, ch, a, grad_scale); }); break;
+    default: emu::launch(g, b, [&] { adamw_multi_kernel<float, true>(table, ch, a, grad_scale); }); break;
+  }
   return 0;
 }
 

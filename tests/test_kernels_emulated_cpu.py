@@ -374,3 +374,27 @@ def test_kv_append_and_moe_kernels_emulated(emu2):
     emu2.emu_moe_combine(xs.data_ptr(), slot.data_ptr(), wts.data_ptr(), out.data_ptr(), T, topk, Hd)
     want = (xs[slot.long()].view(T, topk, Hd).float() * wts[..., None]).sum(1)
     torch.testing.assert_close(out.float(), want, atol=2e-2, rtol=1.6e-2)
+
+
+@pytest.mark.timeout(300)
+def test_adamw_master_weights_kernel_emulated(emu):
+    """fp32 master parameters: ten tiny updates that bf16 alone would drop entirely must accumulate in the master copy, and the
+    bf16 parameter must always be the rounding of the master."""
+    from oracle import adamw_oracle as O
+
+    torch.manual_seed(7)
+    n = 8 * 40 + 3
+    master = torch.randn(n)
+    pb = master.to(BF)
+    m, v = torch.zeros(n, dtype=BF), torch.zeros(n, dtype=BF)
+    ref_p, ref_m, ref_v = master.clone(), torch.zeros(n), torch.zeros(n)
+    lr = 1e-5  # lr * sign-ish update << bf16 ulp of O(1) parameters
+    for step in range(1, 11):
+        g = torch.randn(n).to(BF)
+        table = torch.tensor([[pb.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, master.data_ptr()]], dtype=torch.int64)
+        cmap = torch.tensor([[0, 0]], dtype=torch.int32)
+        emu.emu_adamw(table.data_ptr(), cmap.data_ptr(), 1, 2, lr, 0.9, 0.95, 1e-8, 0.0, 1 - 0.9 ** step, math.sqrt(1 - 0.95 ** step), None)
+        ref_p, ref_m, ref_v = O.adamw_step(ref_p, g, ref_m, ref_v, step, lr, 0.9, 0.95, 1e-8, 0.0)
+        assert torch.equal(pb, master.to(BF))
+    assert (master - master.to(BF).float()).abs().max() > 0  # the master really carries sub-ulp information
+    torch.testing.assert_close(master, ref_p, atol=2e-6, rtol=1e-4)  # moments are bf16 here, the oracle's are fp32

@@ -156,3 +156,29 @@ def test_optimizer_fails_loudly_without_a_device():
     p.grad = torch.ones(16, dtype=torch.bfloat16)
     with pytest.raises(B200Error):
         B200AdamW([p]).step()
+
+
+def test_b200_adamw_master_weights_follow_fp32_adamw(fakes):
+    """bf16 parameters + fp32 masters: the masters must track torch.optim.AdamW run in fp32 on the same gradients, while a
+    plain bf16 run loses the small updates."""
+    a = _params(torch.float32)
+    b = [torch.nn.Parameter(p.detach().to(torch.bfloat16)) for p in a]
+    for p, q in zip(a, b):
+        p.data.copy_(q.detach().float())  # same starting point (bf16-representable)
+    ref = torch.optim.AdamW(a, lr=1e-5, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.0)
+    ours = fakes.B200AdamW(b, lr=1e-5, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.0, master_weights=True, state_dtype=torch.float32)
+    for step in range(1, 9):
+        _set_grads(b, step)
+        for p, q in zip(a, b):
+            p.grad = q.grad.float()
+        for group in ours.param_groups:
+            for q in group["params"]:
+                st = ours._init_state(q)
+                _fake_ops.register_tensors(q, q.grad, st["exp_avg"], st["exp_avg_sq"], st["master"])
+        ref.step()
+        ours.step()
+    for p, q in zip(a, b):
+        master = ours.state[q]["master"]
+        torch.testing.assert_close(master, p.detach(), atol=1e-6, rtol=1e-5)
+        assert torch.equal(q.detach(), master.to(torch.bfloat16))
+    assert "master" in ours.state_dict()["state"][0]

@@ -8,7 +8,7 @@
 // is the CPU restatement, pinned against torch.optim.AdamW itself in tests/test_optim_cpu.py.
 //
 // All three kernels are HBM-bound streaming passes over every parameter tensor of a param group in ONE launch:
-//   * tensor table (device, int64 [n_tensors][6]): {param*, grad*, exp_avg*, exp_avg_sq*, numel, 0}
+//   * tensor table (device, int64 [n_tensors][6]): {param*, grad*, exp_avg*, exp_avg_sq*, numel, fp32 master param* or 0}
 //   * chunk map   (device, int32 [n_chunks][2]):   {tensor index, chunk index}; a chunk is OPT_CHUNK consecutive elements
 // One CTA per chunk, 16-byte vector accesses whenever the four pointers are 16-byte aligned (always the case for torch
 // allocations and for the row views of a packed weight buffer).  Algorithmic bytes per parameter: AdamW 14 B with bf16
@@ -82,7 +82,9 @@ __device__ __forceinline__ void from_f(float& d, float x) { d = x; }
 
 __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-template <typename ST>
+// MASTER: the update runs on an fp32 master copy of the parameter (table column 5) and the bf16 parameter is its rounding --
+// bf16 alone drops updates smaller than half an ulp (|dp| < 2^-9 |p|), which is most of them late in training.
+template <typename ST, bool MASTER>
 __global__ void __launch_bounds__(OPT_THREADS)
 adamw_multi_kernel(const int64_t* __restrict__ table, const int2* __restrict__ chunks, AdamArgs a,
                    const float* __restrict__ grad_scale) {
@@ -93,20 +95,23 @@ adamw_multi_kernel(const int64_t* __restrict__ table, const int2* __restrict__ c
   ST* m = reinterpret_cast<ST*>(row[2]);
   ST* v = reinterpret_cast<ST*>(row[3]);
   const int64_t n = row[4];
+  float* master = MASTER ? reinterpret_cast<float*>(row[5]) : nullptr;
   const int64_t start = static_cast<int64_t>(ch.y) * OPT_CHUNK;
   const int64_t end = (start + OPT_CHUNK < n) ? start + OPT_CHUNK : n;
   const float gs = grad_scale ? *grad_scale : 1.f;
   int64_t done = start;
-  if (aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v)) {  // OPT_CHUNK % 8 == 0 keeps `start` on a vector boundary
+  if (aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v) && (!MASTER || aligned16(master))) {  // OPT_CHUNK % 8 == 0
     const int64_t vec_end = start + ((end - start) / 8) * 8;
     for (int64_t i = start + threadIdx.x * 8; i < vec_end; i += OPT_THREADS * 8) {
       float fp[8], fg[8], fm[8], fv[8];
-      load8(p + i, fp);
+      if (MASTER) load8(master + i, fp);
+      else load8(p + i, fp);
       load8(g + i, fg);
       load8(m + i, fm);
       load8(v + i, fv);
 #pragma unroll
       for (int e = 0; e < 8; ++e) adamw_update(fp[e], fg[e] * gs, fm[e], fv[e], a);
+      if (MASTER) store8(master + i, fp);
       store8(p + i, fp);
       store8(m + i, fm);
       store8(v + i, fv);
@@ -114,8 +119,9 @@ adamw_multi_kernel(const int64_t* __restrict__ table, const int2* __restrict__ c
     done = vec_end;
   }
   for (int64_t i = done + threadIdx.x; i < end; i += OPT_THREADS) {
-    float fp = __bfloat162float(p[i]), fm = to_f(m[i]), fv = to_f(v[i]);
+    float fp = MASTER ? master[i] : __bfloat162float(p[i]), fm = to_f(m[i]), fv = to_f(v[i]);
     adamw_update(fp, __bfloat162float(g[i]) * gs, fm, fv, a);
+    if (MASTER) master[i] = fp;
     p[i] = __float2bfloat16_rn(fp);
     from_f(m[i], fm);
     from_f(v[i], fv);
@@ -223,6 +229,7 @@ using namespace b200;
 
 extern "C" int b200_optim_chunk_elems(void) { return OPT_CHUNK; }
 
+// state_is_fp32: bit 0 = the moments are fp32 (else bf16), bit 1 = table column 5 holds fp32 master parameters
 extern "C" int b200_adamw_step(const int64_t* tensor_table, const int32_t* chunk_map, int n_chunks, int state_is_fp32,
                                float lr, float beta1, float beta2, float eps, float weight_decay, float bias_correction1,
                                float bias_correction2_sqrt, const float* grad_scale, cudaStream_t stream) {
@@ -233,10 +240,12 @@ extern "C" int b200_adamw_step(const int64_t* tensor_table, const int32_t* chunk
   if (n_chunks == 0) return B200_OK;
   AdamArgs a{lr, beta1, beta2, eps, weight_decay, lr / bias_correction1, 1.f / bias_correction2_sqrt};
   const int2* chunks = reinterpret_cast<const int2*>(chunk_map);
-  if (state_is_fp32)
-    adamw_multi_kernel<float><<<n_chunks, OPT_THREADS, 0, stream>>>(tensor_table, chunks, a, grad_scale);
-  else
-    adamw_multi_kernel<__nv_bfloat16><<<n_chunks, OPT_THREADS, 0, stream>>>(tensor_table, chunks, a, grad_scale);
+  switch (state_is_fp32 & 3) {
+    case 0: adamw_multi_kernel<__nv_bfloat16, false><<<n_chunks, OPT_THREADS, 0, stream>>>(tensor_table, chunks, a, grad_scale); break;
+    case 1: adamw_multi_kernel<float, false><<<n_chunks, OPT_THREADS, 0, stream>>>(tensor_table, chunks, a, grad_scale); break;
+    case 2: adamw_multi_kernel<__nv_bfloat16, true><<<n_chunks, OPT_THREADS, 0, stream>>>(tensor_table, chunks, a, grad_scale); break;
+    default: adamw_multi_kernel<float, true><<<n_chunks, OPT_THREADS, 0, stream>>>(tensor_table, chunks, a, grad_scale); break;
+  }
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }

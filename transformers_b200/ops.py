@@ -446,12 +446,12 @@ def optim_chunk_elems() -> int:
     return int(_lib.load().b200_optim_chunk_elems())
 
 
-def adamw_step(table: torch.Tensor, chunk_map: torch.Tensor, *, state_fp32: bool, lr: float, beta1: float, beta2: float,
+def adamw_step(table: torch.Tensor, chunk_map: torch.Tensor, *, state_fp32: bool, master: bool = False, lr: float, beta1: float, beta2: float,
                eps: float, weight_decay: float, bias_correction1: float, bias_correction2_sqrt: float,
                grad_scale: torch.Tensor | None = None) -> None:
     """One AdamW update of every tensor listed in ``table`` (device int64 [n,6], see include/b200_ops.h), in place."""
     lib = _lib_ready()
-    check(lib.b200_adamw_step(table.data_ptr(), chunk_map.data_ptr(), chunk_map.shape[0], int(state_fp32), float(lr), float(beta1),
+    check(lib.b200_adamw_step(table.data_ptr(), chunk_map.data_ptr(), chunk_map.shape[0], int(state_fp32) | (2 if master else 0), float(lr), float(beta1),
                               float(beta2), float(eps), float(weight_decay), float(bias_correction1),
                               float(bias_correction2_sqrt), grad_scale.data_ptr() if grad_scale is not None else None,
                               _stream()), "b200_adamw_step")

@@ -12,7 +12,9 @@ device and is applied inside the AdamW kernel (no separate scaling pass over the
 ``TrainingArguments.max_grad_norm=0`` then.
 
 Each param group is ONE kernel launch over all its tensors (multi-tensor table, include/b200_ops.h); bf16 parameters and
-gradients, moments in the parameter dtype like torch (or fp32 with ``state_dtype=torch.float32``)."""
+gradients, moments in the parameter dtype like torch (or fp32 with ``state_dtype=torch.float32``); ``master_weights=True``
+keeps an fp32 master copy of every parameter (``state["master"]``) that the update runs on -- bf16 parameters alone lose
+every update below half an ulp."""
 from __future__ import annotations
 
 import math
@@ -27,8 +29,9 @@ def _tables(entries, device):
     """entries: list of (param_ptr, grad_ptr, m_ptr, v_ptr, numel) -> (table int64 [n,6], chunk map int32 [c,2]) on device."""
     chunk = ops.optim_chunk_elems()
     rows, cmap = [], []
-    for i, (p, g, m, v, n) in enumerate(entries):
-        rows.append((p, g, m, v, n, 0))
+    for i, e in enumerate(entries):
+        p, g, m, v, n = e[:5]
+        rows.append((p, g, m, v, n, e[5] if len(e) > 5 else 0))
         cmap.extend((i, c) for c in range((n + chunk - 1) // chunk))
     table = torch.tensor(rows, dtype=torch.int64).reshape(-1, 6)
     cm = torch.tensor(cmap, dtype=torch.int32).reshape(-1, 2)
@@ -71,7 +74,8 @@ def clip_grad_norm_(parameters, max_norm: float, norm_type: float = 2.0) -> torc
 
 class B200AdamW(torch.optim.Optimizer):
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2,
-                 max_grad_norm: float | None = None, state_dtype: torch.dtype | None = None, **unsupported):
+                 max_grad_norm: float | None = None, state_dtype: torch.dtype | None = None, master_weights: bool = False,
+                 **unsupported):
         for k in ("amsgrad", "maximize", "capturable", "differentiable"):
             if unsupported.pop(k, False):
                 raise B200Error(f"B200AdamW: {k}=True is not supported")
@@ -86,6 +90,8 @@ class B200AdamW(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
         self.max_grad_norm = max_grad_norm
         self.state_dtype = state_dtype
+        # fp32 master copy of every parameter (state["master"]): the update runs on it, the bf16 parameter is its rounding
+        self.master_weights = bool(master_weights)
         self.grad_norm = None  # device tensor with the pre-clip global norm of the last step (when max_grad_norm is set)
 
     def _init_state(self, p):
@@ -95,6 +101,8 @@ class B200AdamW(torch.optim.Optimizer):
             st["step"] = torch.tensor(0.0, dtype=torch.float32)
             st["exp_avg"] = torch.zeros_like(p, dtype=dt, memory_format=torch.preserve_format)
             st["exp_avg_sq"] = torch.zeros_like(p, dtype=dt, memory_format=torch.preserve_format)
+            if self.master_weights:
+                st["master"] = p.detach().to(torch.float32, copy=True)
         return st
 
     @torch.no_grad()
@@ -128,12 +136,13 @@ class B200AdamW(torch.optim.Optimizer):
                 if m.dtype != v.dtype or m.dtype not in (torch.float32, p.dtype):
                     raise B200Error("B200AdamW: moments must both be fp32 or both have the parameter dtype")
                 key = (int(st["step"]), m.dtype == torch.float32)
-                launches.setdefault(key, []).append((p.data_ptr(), p.grad.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel()))
+                master = st["master"].data_ptr() if self.master_weights else 0
+                launches.setdefault(key, []).append((p.data_ptr(), p.grad.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), master))
             beta1, beta2 = group["betas"]
             lr = float(group["lr"])  # schedulers write python floats (or 0-dim tensors) into the group
             for (step, fp32), entries in sorted(launches.items()):
                 table, cmap = _tables(entries, device)
-                ops.adamw_step(table, cmap, state_fp32=fp32, lr=lr, beta1=beta1, beta2=beta2, eps=group["eps"],
+                ops.adamw_step(table, cmap, state_fp32=fp32, master=self.master_weights, lr=lr, beta1=beta1, beta2=beta2, eps=group["eps"],
                                weight_decay=group["weight_decay"], bias_correction1=1.0 - beta1 ** step,
                                bias_correction2_sqrt=math.sqrt(1.0 - beta2 ** step), grad_scale=coef)
         return loss
