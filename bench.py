@@ -20,6 +20,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "baseline"))
+from ref_import import import_transformers  # noqa: E402  (reference checkout -> baseline/_ref -> image's transformers)
 
 LLAMA3_8B = dict(vocab_size=128256, hidden_size=4096, intermediate_size=14336, num_hidden_layers=32, num_attention_heads=32,
                  num_key_value_heads=8, head_dim=128, rms_norm_eps=1e-5, max_position_embeddings=8192, attention_bias=False,
@@ -169,7 +171,7 @@ def cpu_reference_sample_stock(seq: int = 1024, repeats: int = 1):
     import torch
 
     try:
-        import transformers
+        transformers = import_transformers()
         from transformers.models.llama.modeling_llama import LlamaDecoderLayer, LlamaRotaryEmbedding
     except Exception:
         return None
@@ -332,7 +334,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     parallelism = args.parallelism or ("tp" if world > 1 else "none")  # north star: shard by the reference tp_plan
 
-    import transformers
+    transformers = import_transformers()
 
     import transformers_b200
     from transformers_b200 import _lib, ops

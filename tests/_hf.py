@@ -1,18 +1,7 @@
-"""Import huggingface/transformers for the boundary tests: the reference checkout when present (authoring container),
-otherwise whatever ``transformers`` is installed (the GPU box has no /root/reference)."""
+"""Import huggingface/transformers for the boundary tests (see baseline/ref_import.py for the search order: reference
+checkout, then the unmodified reference installed under baseline/_ref — which is what the GPU box uses — then the image's)."""
 import os
 import sys
-import types
 
-REF_SRC = "/root/reference/src"
-
-
-def import_transformers():
-    if "transformers" not in sys.modules and os.path.isdir(REF_SRC) and not os.environ.get("B200_USE_INSTALLED_TRANSFORMERS"):
-        sys.path.insert(0, REF_SRC)
-        stub = types.ModuleType("transformers.dependency_versions_check")  # tokenizers version gate
-        stub.dep_version_check = lambda *a, **k: None
-        sys.modules.setdefault("transformers.dependency_versions_check", stub)
-    import transformers
-
-    return transformers
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline"))
+from ref_import import REF_SRC, import_transformers, where  # noqa: E402,F401
