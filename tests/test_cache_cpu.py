@@ -21,6 +21,18 @@ def test_layer_defers_to_reference_update_on_cpu():
         ka, va = a.update(k, v)
         kb, vb = b.update(k, v)
         assert torch.equal(ka, kb) and torch.equal(va, vb)
+        assert a.get_seq_length() == b.get_seq_length() and a.get_mask_sizes(1) == b.get_mask_sizes(1)
+    # bookkeeping follows the reference on the deferred path too (lengths stayed 0, crop / reorder were skipped)
+    assert a.get_seq_length() == 5
+    idx = torch.tensor([1, 0])
+    for op in (lambda l: l.crop(-2), lambda l: l.reorder_cache(idx), lambda l: l.batch_repeat_interleave(2),
+               lambda l: l.batch_select_indices(torch.tensor([0, 3])), lambda l: l.crop(0)):
+        op(a)
+        op(b)
+        assert a.get_seq_length() == b.get_seq_length() and torch.equal(a.keys, b.keys) and torch.equal(a.values, b.values)
+    a.reset()
+    b.reset()
+    assert a.get_seq_length() == b.get_seq_length()
 
 
 def test_make_cache_replaces_only_full_attention_layers():

@@ -325,3 +325,90 @@ def test_gemma_v1_blocks_run_on_the_kernel_path():
     _compare(ref, ours, torch.randint(1, 160, (2, 20)), atol=5e-5)
     names = [c[0] for c in _fake_ops.CALLS]
     assert names.count("attn_fwd") == 2 and names.count("glu_fwd") == 2
+
+
+# ------------------------------------------------------------------------------------------- packed (varlen) batches
+def _packed_position_ids(lengths):
+    return torch.cat([torch.arange(n) for n in lengths])[None]
+
+
+@pytest.mark.parametrize("cls_cfg", ["llama", "mistral_window"])
+def test_packed_batch_from_position_ids_matches_stock_eager(cls_cfg):
+    """Padding-free packed batch: position_ids restart at every sequence boundary (what DataCollatorWithFlattening emits).
+    The reference composes the sequence indices into the mask function (masking_utils.py:728-757,973-974); the b200 mask
+    entry must hand them on and attention must stay inside each sequence (round-1 bug: it attended across boundaries).
+    Mirrors the flash path's packed handling, modeling_flash_attention_utils.py:536,796-822."""
+    if cls_cfg == "llama":
+        ref, ours = _pair(transformers.LlamaForCausalLM, _llama_cfg())
+    else:
+        cfg = transformers.MistralConfig(vocab_size=160, hidden_size=64, intermediate_size=176, num_hidden_layers=2,
+                                         num_attention_heads=4, num_key_value_heads=2, head_dim=16, sliding_window=5,
+                                         max_position_embeddings=128)
+        ref, ours = _pair(transformers.MistralForCausalLM, cfg)
+    lengths = [7, 1, 11, 5]
+    torch.manual_seed(2)
+    ids = torch.randint(0, 160, (1, sum(lengths)))
+    pos = _packed_position_ids(lengths)
+    kw = dict(input_ids=ids, position_ids=pos, labels=ids, use_cache=False)
+    a = ref(**kw)
+    a.loss.backward()
+    _fake_ops.CALLS.clear()
+    b = ours(**kw)
+    b.loss.backward()
+    torch.testing.assert_close(b.logits, a.logits, atol=2e-5, rtol=1e-4)
+    ga = dict(ref.named_parameters())
+    for n, p in ours.named_parameters():
+        torch.testing.assert_close(p.grad, ga[n].grad, atol=2e-5, rtol=1e-3, msg=lambda m, n=n: f"{n}: {m}")
+    names = [c[0] for c in _fake_ops.CALLS]
+    assert names.count("attn_fwd") == 2 * len(lengths) and names.count("attn_bwd") == 2 * len(lengths)  # one launch per sequence
+    # and the un-packed answer is different (the test would not notice a regression otherwise)
+    c = ref(input_ids=ids, labels=ids, use_cache=False)
+    assert (c.logits - a.logits).abs().max() > 1e-3
+
+
+def test_packed_batch_two_rows_and_cu_seq_lens_kwargs():
+    """(1) batch size 2, each row packed differently (find_packed_sequence_indices handles any batch size);
+    (2) explicit cu_seq_lens_* kwargs of a flattened batch (modeling_flash_attention_utils.py:570-590) without the mask
+    entry seeing a position reset (attention function called directly)."""
+    ref, ours = _pair(transformers.LlamaForCausalLM, _llama_cfg())
+    torch.manual_seed(3)
+    ids = torch.randint(0, 160, (2, 16))
+    pos = torch.stack([_packed_position_ids([4, 12])[0], _packed_position_ids([9, 3, 4])[0]])
+    a = ref(input_ids=ids, position_ids=pos, use_cache=False).logits
+    b = ours(input_ids=ids, position_ids=pos, use_cache=False).logits
+    torch.testing.assert_close(b, a, atol=2e-5, rtol=1e-4)
+
+    from transformers_b200.integration import b200_attention_forward
+
+    B, H, S, D = 1, 2, 12, 16
+    q, k, v = (torch.randn(B, H, S, D) for _ in range(3))
+    cu = torch.tensor([0, 5, 6, 12], dtype=torch.int32)
+    mod = torch.nn.Module()
+    mod.is_causal = True
+    out, _ = b200_attention_forward(mod, q, k, v, None, cu_seq_lens_q=cu, cu_seq_lens_k=cu, max_length_q=6, max_length_k=6)
+    want = torch.cat([torch.nn.functional.scaled_dot_product_attention(q[:, :, s:e], k[:, :, s:e], v[:, :, s:e], is_causal=True)
+                      for s, e in ((0, 5), (5, 6), (6, 12))], dim=2).transpose(1, 2)
+    torch.testing.assert_close(out, want, atol=1e-5, rtol=1e-5)
+    with pytest.raises(transformers_b200.B200Error):
+        b200_attention_forward(mod, q, k, v, None, cu_seq_lens_q=torch.tensor([0, 5, 11]), cu_seq_lens_k=torch.tensor([0, 5, 11]))
+
+
+def test_masks_the_kernels_cannot_express_raise():
+    """Interior zeros in a padding mask and mask overlays other than causal / window / packed are refused loudly."""
+    from transformers.masking_utils import and_masks, causal_mask_function, chunked_overlay, or_masks
+
+    from transformers_b200.integration import b200_attention_mask
+    from transformers_b200.modules import mask_to_kv_ranges
+
+    holes = torch.tensor([[1, 1, 0, 1, 1, 0]], dtype=torch.bool)
+    with pytest.raises(transformers_b200.B200Error):
+        mask_to_kv_ranges(holes)
+    ok = torch.tensor([[0, 0, 1, 1, 1, 0], [0, 0, 0, 0, 0, 0]], dtype=torch.bool)
+    s, e = mask_to_kv_ranges(ok)
+    assert s.tolist() == [2, 0] and e.tolist() == [5, 0]
+    assert mask_to_kv_ranges(ok)[0] is s  # cached on the tensor object: one validation per forward, not per layer
+    assert b200_attention_mask(1, 6, 6, mask_function=causal_mask_function) is None
+    for fn in (or_masks(causal_mask_function, causal_mask_function),
+               and_masks(chunked_overlay(4, torch.zeros(1, dtype=torch.int64)), causal_mask_function)):
+        with pytest.raises(transformers_b200.B200Error):
+            b200_attention_mask(1, 6, 6, mask_function=fn)

@@ -182,3 +182,50 @@ def test_b200_adamw_master_weights_follow_fp32_adamw(fakes):
         torch.testing.assert_close(master, p.detach(), atol=1e-6, rtol=1e-5)
         assert torch.equal(q.detach(), master.to(torch.bfloat16))
     assert "master" in ours.state_dict()["state"][0]
+
+
+def test_state_dict_round_trip_keeps_state_dtypes(fakes):
+    """torch's Optimizer.load_state_dict casts floating-point state to the parameter dtype (bf16); the fp32 master copy and
+    fp32 moments must come back as fp32 (the kernel reads them as float*), bit for bit."""
+    b = [torch.nn.Parameter(p.detach().to(torch.bfloat16)) for p in _params(torch.float32)]
+    ours = fakes.B200AdamW(b, lr=1e-3, master_weights=True, state_dtype=torch.float32)
+    _set_grads(b, 1)
+    for q in b:
+        st = ours._init_state(q)
+        _fake_ops.register_tensors(q, q.grad, st["exp_avg"], st["exp_avg_sq"], st["master"])
+    ours.step()
+    sd = ours.state_dict()
+    fresh = fakes.B200AdamW(b, lr=1e-3, master_weights=True, state_dtype=torch.float32)
+    fresh.load_state_dict(sd)
+    for q in b:
+        for key in ("exp_avg", "exp_avg_sq", "master"):
+            got, want = fresh.state[q][key], ours.state[q][key]
+            assert got.dtype == torch.float32 and torch.equal(got, want) and got.data_ptr() != want.data_ptr()
+    # a corrupted state (what the un-overridden load_state_dict produced) is refused before any pointer is taken
+    fresh.state[b[0]]["master"] = fresh.state[b[0]]["master"].to(torch.bfloat16)
+    _set_grads(b, 2)
+    with pytest.raises(fakes.B200Error):
+        fresh.step()
+
+
+def test_step_invalidates_the_fused_weight_cache(fakes):
+    """The kernels write parameters through raw pointers; modules.fused_weight keys its q|k|v / gate|up concatenations on
+    Tensor._version, so step() must bump it or every later forward would run on the pre-training weights."""
+    from transformers_b200.modules import fused_weight
+
+    ps = [torch.nn.Parameter(torch.randn(4, 8)) for _ in range(2)]
+    holder = torch.nn.Module()
+    before = fused_weight(holder, "gate_up", ps).clone()
+    assert fused_weight(holder, "gate_up", ps) is fused_weight(holder, "gate_up", ps)  # cached while nothing changes
+    opt = fakes.B200AdamW(ps, lr=0.1)
+    _set_grads(ps, 1)
+    _register(opt)
+    v0 = [p._version for p in ps]
+    opt.step()
+    assert all(p._version > v for p, v in zip(ps, v0))
+    after = fused_weight(holder, "gate_up", ps)
+    assert not torch.equal(after, before) and torch.equal(after, torch.cat([p.detach() for p in ps]))
+    g0 = [p.grad._version for p in ps]
+    _fake_ops.register_tensors(*[p.grad for p in ps])
+    fakes.clip_grad_norm_(ps, 1e-3)
+    assert all(p.grad._version > v for p, v in zip(ps, g0))

@@ -66,12 +66,24 @@ def _make_layer_class():
             self.values = self._buf_v[:, :, : self._len]
             return self.keys, self.values
 
+        def _stock(self) -> bool:
+            """True while this layer is running on the reference's own ``torch.cat`` path (``update`` deferred to the base
+            class: CPU tensors, or a dtype the kernels do not take): every bookkeeping method then defers too, so that
+            lengths, mask sizes, crop and beam re-ordering keep following ``self.keys`` / ``self.values``."""
+            return getattr(self, "_buf_k", None) is None
+
         def get_seq_length(self) -> int:
-            return getattr(self, "_len", 0) if self.is_initialized else 0
+            if self._stock():
+                return super().get_seq_length()
+            return self._len if self.is_initialized else 0
 
         def crop(self, tokens_to_remove: int = 0, **kw) -> None:
-            if not self.is_initialized or self._buf_k is None:
+            """cache_utils.py:166-189: negative = remove that many tokens, positive (deprecated) = absolute final length,
+            0 = nothing to do."""
+            if not self.is_initialized:
                 return
+            if self._stock():
+                return super().crop(kw.get("max_length", tokens_to_remove))
             n = kw.get("max_length", tokens_to_remove)
             new_len = self._len - abs(n) if n < 0 else min(self._len, n if n > 0 else self._len)
             self._len = max(0, new_len)
@@ -79,6 +91,8 @@ def _make_layer_class():
             self.values = self._buf_v[:, :, : self._len]
 
         def reset(self) -> None:
+            if self._stock():
+                return super().reset()
             if self.is_initialized:
                 self._len = 0
                 if self._buf_k is not None:
@@ -91,14 +105,20 @@ def _make_layer_class():
             self.values = self._buf_v[:, :, : self._len]
 
         def reorder_cache(self, beam_idx) -> None:
+            if self._stock():
+                return super().reorder_cache(beam_idx)
             if self.get_seq_length() > 0:
                 self._rebuffer(self._buf_k.index_select(0, beam_idx.to(self.device)), self._buf_v.index_select(0, beam_idx.to(self.device)))
 
         def batch_repeat_interleave(self, repeats: int) -> None:
+            if self._stock():
+                return super().batch_repeat_interleave(repeats)
             if self.get_seq_length() > 0:
                 self._rebuffer(self._buf_k.repeat_interleave(repeats, dim=0), self._buf_v.repeat_interleave(repeats, dim=0))
 
         def batch_select_indices(self, indices) -> None:
+            if self._stock():
+                return super().batch_select_indices(indices)
             if self.get_seq_length() > 0:
                 self._rebuffer(self._buf_k[indices, ...], self._buf_v[indices, ...])
 

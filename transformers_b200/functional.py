@@ -293,6 +293,41 @@ class GluFn(torch.autograd.Function):
         return ops.glu_bwd(dh, gu, ctx.gelu), None
 
 
+def _attn_fwd_any(q, k, v, scale, causal, window, softcap, kv_start, kv_end, segments):
+    """Attention forward over [B, S, h, D] views.  ``segments`` (packed batch: [[(start, end), ...] per row]) runs the
+    kernel once per sequence on row slices of the same buffers -- varlen attention without un-padding copies, the way
+    the reference's flash path calls flash_attn_varlen_func (modeling_flash_attention_utils.py:796-822).
+    Returns (out, [lse, ...])."""
+    if segments is None:
+        out, lse = ops.attn_fwd(q, k, v, scale=scale, causal=causal, window=window, softcap=softcap, kv_start=kv_start,
+                                kv_end=kv_end)
+        return out, [lse]
+    if q.shape[1] != k.shape[1]:
+        raise ops.B200Error("b200 attention: packed batches need q_len == kv_len (no KV cache)")
+    out = torch.empty(q.shape, device=q.device, dtype=q.dtype)
+    lses = []
+    for b, rows in enumerate(segments):
+        for s, e in rows:
+            _, lse = ops.attn_fwd(q[b:b + 1, s:e], k[b:b + 1, s:e], v[b:b + 1, s:e], scale=scale, causal=causal, window=window,
+                                  softcap=softcap, out=out[b:b + 1, s:e])
+            lses.append(lse)
+    return out, lses
+
+
+def _attn_bwd_any(q, k, v, out, dout, lses, dq, dk, dv, scale, causal, window, softcap, kv_start, kv_end, segments):
+    if segments is None:
+        ops.attn_bwd(q, k, v, out, dout, lses[0], dq, dk, dv, scale=scale, causal=causal, window=window, softcap=softcap,
+                     kv_start=kv_start, kv_end=kv_end)
+        return
+    i = 0
+    for b, rows in enumerate(segments):
+        for s, e in rows:
+            sl = (slice(b, b + 1), slice(s, e))
+            ops.attn_bwd(q[sl], k[sl], v[sl], out[sl], dout[sl], lses[i], dq[sl], dk[sl], dv[sl], scale=scale, causal=causal,
+                         window=window, softcap=softcap)
+            i += 1
+
+
 class QKVRopeAttentionFn(torch.autograd.Function):
     """Fused attention block up to (not including) o_proj, LlamaAttention.forward models/llama/modeling_llama.py:251-279:
     packed QKV projection (one GEMM) -> RoPE in place on the private projection buffer (apply_rotary_pos_emb :138-160)
@@ -300,9 +335,10 @@ class QKVRopeAttentionFn(torch.autograd.Function):
     Backward: attention bwd writes dq|dk|dv straight into one packed buffer -> RoPE^T in place -> dgrad + wgrad GEMMs."""
 
     @staticmethod
-    def forward(ctx, x, w_fused, cos, sin, cfg, kv_start, kv_end, tp, *weights):
+    def forward(ctx, x, w_fused, cos, sin, cfg, kv_start, kv_end, tp, segments, *weights):
         Hq, Hkv, D, scale, causal, window, softcap = cfg
         ctx.tp = tp
+        ctx.segments = segments
         _, mode, st = _tp_unpack(tp)
         K = x.shape[-1]
         x2 = x.reshape(-1, K)
@@ -319,9 +355,8 @@ class QKVRopeAttentionFn(torch.autograd.Function):
         q = qkv[..., : Hq * D].view(B, S, Hq, D)
         k = qkv[..., Hq * D:(Hq + Hkv) * D].view(B, S, Hkv, D)
         v = qkv[..., (Hq + Hkv) * D:].view(B, S, Hkv, D)
-        out, lse = ops.attn_fwd(q, k, v, scale=scale, causal=causal, window=window, softcap=softcap, kv_start=kv_start,
-                                kv_end=kv_end)
-        ctx.save_for_backward(x2, w_fused, qkv, out, lse, cos, sin, kv_start, kv_end)
+        out, lses = _attn_fwd_any(q, k, v, scale, causal, window, softcap, kv_start, kv_end, segments)
+        ctx.save_for_backward(x2, w_fused, qkv, out, cos, sin, kv_start, kv_end, *lses)
         ctx.cfg = cfg
         ctx.splits = [w.shape[0] for w in weights]
         ctx.x_shape = x.shape
@@ -329,7 +364,7 @@ class QKVRopeAttentionFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
-        x2, w_fused, qkv, out, lse, cos, sin, kv_start, kv_end = ctx.saved_tensors
+        x2, w_fused, qkv, out, cos, sin, kv_start, kv_end, *lses = ctx.saved_tensors
         Hq, Hkv, D, scale, causal, window, softcap = ctx.cfg
         B, S, W = qkv.shape
         q = qkv[..., : Hq * D].view(B, S, Hq, D)
@@ -342,8 +377,7 @@ class QKVRopeAttentionFn(torch.autograd.Function):
         dq = dqkv[..., : Hq * D].view(B, S, Hq, D)
         dk = dqkv[..., Hq * D:(Hq + Hkv) * D].view(B, S, Hkv, D)
         dv = dqkv[..., (Hq + Hkv) * D:].view(B, S, Hkv, D)
-        ops.attn_bwd(q, k, v, out, dout4, lse, dq, dk, dv, scale=scale, causal=causal, window=window, softcap=softcap,
-                     kv_start=kv_start, kv_end=kv_end)
+        _attn_bwd_any(q, k, v, out, dout4, lses, dq, dk, dv, scale, causal, window, softcap, kv_start, kv_end, ctx.segments)
         ops.rope_(dqkv, cos, sin, Hq + Hkv, D, backward=True)
         d2 = dqkv.view(B * S, W)
         _, mode, st = _tp_unpack(ctx.tp)
@@ -356,11 +390,11 @@ class QKVRopeAttentionFn(torch.autograd.Function):
             dx = ops.gemm(d2, w_fused, b_mn=True).view(ctx.x_shape)
             work = _tp_reduce_async(dx, ctx.tp[0]) if ctx.tp is not None else None  # overlaps the wgrad
         grads_w = [None] * len(ctx.splits)
-        if any(ctx.needs_input_grad[8:]):
+        if any(ctx.needs_input_grad[9:]):
             dw = ops.gemm(d2, x2, a_mn=True, b_mn=True)
             off = 0
             for i, n in enumerate(ctx.splits):
-                if ctx.needs_input_grad[8 + i]:
+                if ctx.needs_input_grad[9 + i]:
                     grads_w[i] = dw[off:off + n]
                 off += n
         if work is not None:
@@ -368,7 +402,7 @@ class QKVRopeAttentionFn(torch.autograd.Function):
         for w_ in works:
             w_.wait()
         del keep
-        return (dx, None, None, None, None, None, None, None, *grads_w)
+        return (dx, None, None, None, None, None, None, None, None, *grads_w)
 
 
 class FlashAttentionFn(torch.autograd.Function):
@@ -376,24 +410,22 @@ class FlashAttentionFn(torch.autograd.Function):
     (AttentionInterface signature, docs/source/en/attention_interface.md:164-175) incl. the KV-cache / decode path."""
 
     @staticmethod
-    def forward(ctx, q, k, v, scale, causal, window, softcap, kv_start, kv_end):
-        out, lse = ops.attn_fwd(q, k, v, scale=scale, causal=causal, window=window, softcap=softcap, kv_start=kv_start,
-                                kv_end=kv_end)
-        ctx.save_for_backward(q, k, v, out, lse, kv_start, kv_end)
-        ctx.cfg = (scale, causal, window, softcap)
+    def forward(ctx, q, k, v, scale, causal, window, softcap, kv_start, kv_end, segments=None):
+        out, lses = _attn_fwd_any(q, k, v, scale, causal, window, softcap, kv_start, kv_end, segments)
+        ctx.save_for_backward(q, k, v, out, kv_start, kv_end, *lses)
+        ctx.cfg = (scale, causal, window, softcap, segments)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        q, k, v, out, lse, kv_start, kv_end = ctx.saved_tensors
-        scale, causal, window, softcap = ctx.cfg
+        q, k, v, out, kv_start, kv_end, *lses = ctx.saved_tensors
+        scale, causal, window, softcap, segments = ctx.cfg
         dout = dout.contiguous()
         dq = torch.empty(q.shape, device=q.device, dtype=q.dtype)
         dk = torch.empty(k.shape, device=k.device, dtype=k.dtype)
         dv = torch.empty(v.shape, device=v.device, dtype=v.dtype)
-        ops.attn_bwd(q, k, v, out, dout, lse, dq, dk, dv, scale=scale, causal=causal, window=window, softcap=softcap,
-                     kv_start=kv_start, kv_end=kv_end)
-        return dq, dk, dv, None, None, None, None, None, None
+        _attn_bwd_any(q, k, v, out, dout, lses, dq, dk, dv, scale, causal, window, softcap, kv_start, kv_end, segments)
+        return dq, dk, dv, None, None, None, None, None, None, None
 
 
 class QKVRopeFn(torch.autograd.Function):

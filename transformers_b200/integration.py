@@ -36,8 +36,6 @@ def b200_attention_forward(module, query, key, value, attention_mask, dropout: f
         raise B200Error("b200 attention: dropout is not supported")
     if kwargs.get("s_aux") is not None:
         raise B200Error("b200 attention: attention sinks (s_aux) are not supported")
-    if kwargs.get("cu_seq_lens_q") is not None:
-        raise B200Error("b200 attention: packed (varlen) batches are not supported yet")
     if query.stride(-1) != 1:
         query = query.contiguous()
     if key.stride(-1) != 1:
@@ -51,25 +49,56 @@ def b200_attention_forward(module, query, key, value, attention_mask, dropout: f
         is_causal = getattr(module, "is_causal", True)
     # decode (q_len 1 over the whole cache) needs no causal mask (integrations/sdpa_attention.py:124)
     causal = bool(is_causal) and Sq > 1
-    kv_start, kv_end = M.mask_to_kv_ranges(attention_mask)
-    if attention_mask is not None and attention_mask.shape[1] != key.shape[2]:
+    kv_start, kv_end, segments = M.mask_info(attention_mask, kwargs, query.shape[0] * Sq)
+    if segments is not None and (len(segments) != query.shape[0] or key.shape[2] != Sq):
+        raise B200Error("b200 attention: packed batches need one range list per row and q_len == kv_len (no KV cache)")
+    if torch.is_tensor(attention_mask) and attention_mask.shape[1] != key.shape[2]:
         raise B200Error("b200 attention: padding mask length does not match the kv length")
     q = query.transpose(1, 2)  # [B, S, h, D] views; no copies
     k = key.transpose(1, 2)
     v = value.transpose(1, 2)
     out = Fn.FlashAttentionFn.apply(q, k, v, float(scaling), causal, int(sliding_window or 0), float(softcap or 0.0),
-                                    kv_start, kv_end)
+                                    kv_start, kv_end, segments)
     return out, None
+
+
+def _packed_ids_of(mask_function):
+    """Walk the mask function the reference composed (masking_utils.py:864-996) and return the packed-sequence index
+    tensor it carries, if any.  Patterns the kernels compute from indices pass (causal, sliding-window overlay -- the
+    window itself comes from the attention module); patterns they cannot express raise instead of being ignored."""
+    if mask_function is None:
+        return None
+    name = getattr(mask_function, "__qualname__", type(mask_function).__name__)
+    cells = dict(zip(getattr(getattr(mask_function, "__code__", None), "co_freevars", ()),
+                     (c.cell_contents for c in (getattr(mask_function, "__closure__", None) or ()))))
+    if name == "causal_mask_function" or name.startswith("sliding_window_overlay.<locals>"):
+        return None
+    if name.startswith("packed_sequence_mask_function.<locals>"):
+        return cells["packed_sequence_mask"]
+    if name.startswith("and_masks.<locals>"):
+        found = [t for t in (_packed_ids_of(f) for f in cells["mask_functions"]) if t is not None]
+        if len(found) > 1:
+            raise B200Error("b200 attention mask: more than one packed-sequence overlay")
+        return found[0] if found else None
+    raise B200Error(f"b200 attention mask: the mask pattern `{name}` cannot be expressed by the b200 kernels (supported: "
+                    "causal, sliding window, left / right padding, packed sequences)")
 
 
 def b200_attention_mask(batch_size, q_length, kv_length, q_offset=0, kv_offset=0, mask_function=None, attention_mask=None,
                         **kwargs):
     """AttentionMaskInterface entry: like the flash backends (masking_utils.py:607-647) return the 2-D padding mask, or
-    None when nothing is padded; causal / sliding patterns are computed inside the kernel."""
+    None when nothing is padded; causal / sliding patterns are computed inside the kernel.  When the reference detected a
+    padding-free packed batch (position_ids that restart, masking_utils.py:728-757) it composes the sequence indices into
+    ``mask_function`` (:973-974); they are handed on as ``modules.SegmentIds`` so attention stays inside each sequence."""
+    packed = _packed_ids_of(mask_function)
     if attention_mask is not None:
         attention_mask = attention_mask[:, -kv_length:]
         if attention_mask.shape[1] == kv_length and attention_mask.all():
             attention_mask = None
+    if packed is not None:
+        if attention_mask is not None or q_length != kv_length:
+            raise B200Error("b200 attention mask: packed sequences together with padding or a KV cache are not supported")
+        return M.SegmentIds(packed)
     return attention_mask
 
 

@@ -122,17 +122,83 @@ def _check_no_bias(*linears):
 
 def mask_to_kv_ranges(attention_mask: torch.Tensor | None):
     """2-D padding mask [B, kv_len] (what our AttentionMaskInterface entry returns) -> int32 (kv_start, kv_end).
-    Padding must be contiguous on the left and/or right of each row (what tokenizers produce)."""
+    Padding must be contiguous on the left and/or right of each row (what tokenizers produce); a mask with interior zeros
+    (concatenated samples, custom masks) cannot be expressed as one range per row and raises instead of silently
+    attending across the holes.  The result is cached on the mask tensor object: the reference hands the same object to
+    every decoder layer of a forward, so the validation (one host sync) runs once per forward, not once per layer."""
     if attention_mask is None:
         return None, None
     if attention_mask.dim() != 2:
         raise B200Error(f"b200 attention expects a 2-D padding mask or None, got shape {tuple(attention_mask.shape)}")
+    hit = attention_mask.__dict__.get("_b200_ranges")
+    if hit is not None and hit[0] == attention_mask._version:
+        return hit[1], hit[2]
     m = attention_mask.to(torch.bool)
     L = m.shape[1]
     idx = torch.arange(L, device=m.device)
-    start = torch.where(m, idx, L).amin(dim=1).to(torch.int32)
-    end = (torch.where(m, idx, -1).amax(dim=1) + 1).to(torch.int32)
-    return start.contiguous(), end.contiguous()
+    start = torch.where(m, idx, L).amin(dim=1)
+    end = torch.where(m, idx, -1).amax(dim=1) + 1
+    count = m.sum(dim=1)
+    if bool((count != (end - start).clamp(min=0)).any()):
+        raise B200Error("b200 attention: the padding mask has zeros between valid tokens; only left / right padding is "
+                        "supported (packed batches are recognised through position_ids or cu_seq_lens_*)")
+    empty = count == 0  # fully masked row: an empty range (the row's output is zero, as for the un-padding flash path)
+    start = torch.where(empty, torch.zeros_like(start), start).to(torch.int32).contiguous()
+    end = torch.where(empty, torch.zeros_like(end), end).to(torch.int32).contiguous()
+    attention_mask.__dict__["_b200_ranges"] = (attention_mask._version, start, end)
+    return start, end
+
+
+class SegmentIds:
+    """What our AttentionMaskInterface entry returns for a padding-free packed batch (several sequences concatenated along
+    the sequence axis, recognised by the reference from position_ids that restart: masking_utils.py:728-757,973-974):
+    the [B, S] tensor of sequence indices plus, lazily, the per-row (start, end) token ranges on the host.  It travels
+    through the decoder layers in the ``attention_mask`` slot, like the 2-D mask of the flash backends."""
+
+    def __init__(self, ids: torch.Tensor | None = None, ranges: list | None = None):
+        self.ids, self._ranges = ids, ranges
+
+    @classmethod
+    def from_cu_seqlens(cls, cu, total: int):
+        """cu_seq_lens_q of a flattened batch (modeling_flash_attention_utils.py:570-590): [n + 1] cumulative lengths."""
+        c = [int(v) for v in (cu.tolist() if torch.is_tensor(cu) else cu)]
+        if len(c) < 2 or c[0] != 0 or c[-1] != total or any(b < a for a, b in zip(c, c[1:])):
+            raise B200Error(f"b200 attention: cu_seq_lens {c} do not partition the {total} tokens of the batch")
+        return cls(None, [[(a, b) for a, b in zip(c, c[1:]) if b > a]])
+
+    def ranges(self) -> list:
+        """[[(start, end), ...] per batch row]; one host sync, once per forward (cached)."""
+        if self._ranges is None:
+            ids = self.ids
+            B, S = ids.shape
+            cuts = (ids[:, 1:] != ids[:, :-1]).nonzero().tolist()
+            rows = [[0] for _ in range(B)]
+            for b, i in cuts:
+                rows[b].append(i + 1)
+            self._ranges = [[(a, e) for a, e in zip(r, r[1:] + [S])] for r in rows]
+        return self._ranges
+
+
+def mask_info(attention_mask, kwargs=None, total_tokens=None):
+    """What the attention kernels need from the ``attention_mask`` slot and the flash-style kwargs:
+    (kv_start, kv_end, segments) -- per-row padding ranges (2-D bool mask), or the packed-sequence ranges."""
+    if isinstance(attention_mask, SegmentIds):
+        return None, None, attention_mask.ranges()
+    cu_q = (kwargs or {}).get("cu_seq_lens_q")
+    if cu_q is not None:
+        cu_k = kwargs.get("cu_seq_lens_k")
+        if attention_mask is not None:
+            raise B200Error("b200 attention: cu_seq_lens_* together with a padding mask is not supported")
+        seg = cu_q.__dict__.get("_b200_segments") if torch.is_tensor(cu_q) else None
+        if seg is None:
+            if cu_k is not None and cu_k is not cu_q and not torch.equal(torch.as_tensor(cu_k), torch.as_tensor(cu_q)):
+                raise B200Error("b200 attention: cu_seq_lens_q and cu_seq_lens_k differ (cross-length packing is not supported)")
+            seg = SegmentIds.from_cu_seqlens(cu_q, total_tokens)
+            if torch.is_tensor(cu_q):
+                cu_q.__dict__["_b200_segments"] = seg  # the same tensor reaches every layer: one sync per forward
+        return None, None, seg.ranges()
+    kv_start, kv_end = mask_to_kv_ranges(attention_mask)
+    return kv_start, kv_end, None
 
 
 # ------------------------------------------------------------------------------------------------------------ mixins
@@ -191,10 +257,16 @@ class B200AttentionMixin:
         window = self._b200_window() or 0
         softcap = getattr(self, "attn_logit_softcapping", None) or 0.0
         wqkv = fused_weight(self, "qkv", [wq, wk, wv])
+        if kwargs.get("s_aux") is not None:
+            raise B200Error("b200 attention: attention sinks (s_aux) are not supported")
         if past_key_values is None:
-            kv_start, kv_end = mask_to_kv_ranges(attention_mask)
+            # padding ranges, or the sequence ranges of a padding-free packed batch (position_ids that restart reach us as
+            # SegmentIds through our mask entry; collators that flatten pass cu_seq_lens_* instead)
+            kv_start, kv_end, segments = mask_info(attention_mask, kwargs, B * S)
+            if segments is not None and len(segments) != B:
+                raise B200Error("b200 attention: cu_seq_lens_* describe a flattened batch (batch size 1)")
             cfg = (Hq, Hkv, D, float(self.scaling), True, int(window), float(softcap))
-            attn = Fn.QKVRopeAttentionFn.apply(hidden_states, wqkv, cos, sin, cfg, kv_start, kv_end, col, wq, wk, wv)
+            attn = Fn.QKVRopeAttentionFn.apply(hidden_states, wqkv, cos, sin, cfg, kv_start, kv_end, col, segments, wq, wk, wv)
         else:
             from .integration import b200_attention_forward
 

@@ -69,7 +69,15 @@ def clip_grad_norm_(parameters, max_norm: float, norm_type: float = 2.0) -> torc
     table, cmap = _tables([(0, p.grad.data_ptr(), 0, 0, p.grad.numel()) for p in ps], ps[0].device)
     out = ops.grad_norm(table, cmap, max_norm)
     ops.grad_scale_(table, cmap, out[1:2])
+    _bump_versions([p.grad for p in ps])
     return out[0]
+
+
+def _bump_versions(tensors) -> None:
+    """The kernels write through raw pointers, which autograd's version counters do not see: bump them so that everything
+    keyed on ``_version`` (modules.fused_weight's cached q|k|v and gate|up concatenations, saved-tensor checks) notices the
+    in-place update exactly as it would after ``torch.optim.AdamW.step``."""
+    torch._C._increment_version(list(tensors))
 
 
 class B200AdamW(torch.optim.Optimizer):
@@ -93,6 +101,26 @@ class B200AdamW(torch.optim.Optimizer):
         # fp32 master copy of every parameter (state["master"]): the update runs on it, the bf16 parameter is its rounding
         self.master_weights = bool(master_weights)
         self.grad_norm = None  # device tensor with the pre-clip global norm of the last step (when max_grad_norm is set)
+
+    def load_state_dict(self, state_dict):
+        """``Optimizer.load_state_dict`` casts every floating-point state tensor except ``step`` to the parameter dtype
+        (bf16): an fp32 ``master`` copy or fp32 moments would come back as bf16 while the kernel reads them as ``float*``.
+        Restore them from the incoming state dict itself (no round trip through bf16) in the dtypes this optimizer uses."""
+        from itertools import chain
+
+        super().load_state_dict(state_dict)
+        saved_ids = chain.from_iterable(g["params"] for g in state_dict["param_groups"])
+        params = chain.from_iterable(g["params"] for g in self.param_groups)
+        for sid, p in zip(saved_ids, params):
+            src = state_dict["state"].get(sid)
+            if src is None or p not in self.state:
+                continue
+            for key in ("exp_avg", "exp_avg_sq", "master"):
+                if torch.is_tensor(src.get(key)):
+                    want = torch.float32 if key == "master" else (self.state_dtype or p.dtype)
+                    self.state[p][key] = src[key].detach().to(device=p.device, dtype=want, copy=True).contiguous()
+            if self.master_weights and "master" not in self.state[p]:  # checkpoint written without master weights
+                self.state[p]["master"] = p.detach().to(torch.float32, copy=True)
 
     def _init_state(self, p):
         st = self.state[p]
@@ -136,7 +164,15 @@ class B200AdamW(torch.optim.Optimizer):
                 if m.dtype != v.dtype or m.dtype not in (torch.float32, p.dtype):
                     raise B200Error("B200AdamW: moments must both be fp32 or both have the parameter dtype")
                 key = (int(st["step"]), m.dtype == torch.float32)
-                master = st["master"].data_ptr() if self.master_weights else 0
+                for t in (m, v):
+                    if t.shape != p.shape or t.device != p.device or not t.is_contiguous():
+                        raise B200Error("B200AdamW: optimizer state does not match its parameter (shape / device / layout)")
+                master = 0
+                if self.master_weights:
+                    mw = st.get("master")
+                    if mw is None or mw.dtype != torch.float32 or mw.shape != p.shape or mw.device != p.device or not mw.is_contiguous():
+                        raise B200Error("B200AdamW: state['master'] must be a contiguous fp32 tensor shaped like its parameter")
+                    master = mw.data_ptr()
                 launches.setdefault(key, []).append((p.data_ptr(), p.grad.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), master))
             beta1, beta2 = group["betas"]
             lr = float(group["lr"])  # schedulers write python floats (or 0-dim tensors) into the group
@@ -145,4 +181,5 @@ class B200AdamW(torch.optim.Optimizer):
                 ops.adamw_step(table, cmap, state_fp32=fp32, master=self.master_weights, lr=lr, beta1=beta1, beta2=beta2, eps=group["eps"],
                                weight_decay=group["weight_decay"], bias_correction1=1.0 - beta1 ** step,
                                bias_correction2_sqrt=math.sqrt(1.0 - beta2 ** step), grad_scale=coef)
+            _bump_versions(ps)
         return loss
