@@ -85,6 +85,32 @@ def test_bench_reference_arm_times_stock_layer_even_after_enable(monkeypatch):
     assert bench.cpu_sample(seq=16, repeats=0)[2] == "port"
 
 
+def test_bench_reference_arm_protocol_on_a_tiny_config(monkeypatch, capsys):
+    """`bench.py --impl reference`: 1- and 2-layer stock models through the public API, per-layer time by
+    difference, one JSON line with impl / cpu_baseline / e2e; the model it times contains no B200 class even though the
+    plugin was enabled earlier in this process."""
+    import argparse
+    import json
+
+    import bench
+    import transformers_b200
+    import transformers_b200.integration as integ
+
+    transformers_b200.enable()
+    tiny = dict(bench.LLAMA3_8B, vocab_size=64, hidden_size=64, intermediate_size=128, num_attention_heads=4,
+                num_key_value_heads=2, head_dim=16, num_hidden_layers=3)
+    monkeypatch.setattr(bench, "LLAMA3_8B", tiny)
+    try:
+        bench.run_reference(argparse.Namespace(seq=32, batch=4, steps=2, warmup=1, gpus=1))
+    finally:
+        integ._enabled = False  # the arm clears the patch mapping (it must time stock classes): re-register for later tests
+        transformers_b200.enable()
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "reference" and line["value"] > 0
+    assert "1-layer model" in line["cpu_baseline"]["sample"] and line["e2e"]["value"] == line["value"]
+    assert abs(line["ms_per_step"] - 4 * 32 / line["value"] * 1e3) < 1e-6 * line["ms_per_step"] + 1e-9
+
+
 def test_c_abi_validates_new_entry_points_without_a_gpu():
     import ctypes
 

@@ -208,3 +208,41 @@ def test_switch_back_to_sdpa_same_model():
         c = model(ids).logits.float()
     torch.testing.assert_close(a, b, atol=3e-2, rtol=3e-2)
     assert torch.equal(a, c)
+
+
+def test_packed_batch_equals_separate_sequences():
+    """Padding-free packed batch (position_ids restart at each sequence boundary): logits and gradients must equal those of
+    the sequences run one by one -- attention may not cross a boundary (the reference's flash path:
+    modeling_flash_attention_utils.py:536,796-822; mask path: masking_utils.py:728-757,973-974)."""
+    tf, cfg, model = _build("llama")
+    model.train()
+    lengths = [70, 1, 129, 56]
+    torch.manual_seed(3)
+    ids = torch.randint(1, cfg.vocab_size, (1, sum(lengths)), device="cuda")
+    pos = torch.cat([torch.arange(n) for n in lengths])[None].cuda()
+    model.cuda()
+    labels = ids.clone()
+    ends = torch.tensor(lengths).cumsum(0)
+    labels[0, ends[:-1]] = -100  # the first token of a sequence is not predicted from the previous sequence's last token
+    out = model(input_ids=ids, position_ids=pos, labels=labels, use_cache=False)
+    out.loss.backward()
+    g_packed = {n: p.grad.float().clone() for n, p in model.named_parameters()}
+    model.zero_grad(set_to_none=True)
+    n_targets = sum(n - 1 for n in lengths)
+    s = 0
+    sep_logits, total = [], 0.0
+    for n in lengths:
+        o = model(input_ids=ids[:, s:s + n], labels=ids[:, s:s + n], use_cache=False)
+        sep_logits.append(o.logits)
+        if n > 1:
+            (o.loss * (n - 1) / n_targets).backward()
+            total += o.loss.item() * (n - 1) / n_targets
+        s += n
+    torch.testing.assert_close(out.logits.float(), torch.cat(sep_logits, dim=1).float(), atol=2e-2, rtol=2e-2)
+    assert abs(out.loss.item() - total) < 5e-3
+    for n, p in model.named_parameters():
+        ref = p.grad.float()
+        rel = ((g_packed[n] - ref).abs().max() / (ref.abs().max() + 1e-8)).item()
+        assert rel < 3e-2, f"{n}: {rel}"
+    un = model(input_ids=ids, use_cache=False).logits  # and ignoring the boundaries gives a different answer
+    assert (un.float() - out.logits.float()).abs().max() > 5e-2
