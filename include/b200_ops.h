@@ -52,6 +52,12 @@ int b200_rmsnorm_bwd_workspace_rows(void); /* workspace = fp32[rows * H] */
 int b200_rmsnorm_bwd(const void* dy, const void* x, const void* weight, const float* rstd, void* dx, void* dweight,
                      float* workspace, int T, int H, int gemma, int accumulate_dw, b200_stream_t stream);
 
+/* LlamaRotaryEmbedding.forward (models/llama/modeling_llama.py:113-127): cos / sin bf16 [rows, D] with
+ * cos[r, j] = cos[r, j + D/2] = bf16(cosf(inv_freq[j] * float(position_ids[r])) * attention_scaling); inv_freq fp32 [D/2],
+ * position_ids int64 [rows = B * S].  Bit-exact against the reference's six torch ops. */
+int b200_rope_table(const float* inv_freq, const int64_t* position_ids, void* cos_t, void* sin_t, int rows, int D,
+                    float attention_scaling, b200_stream_t stream);
+
 /* apply_rotary_pos_emb (models/llama/modeling_llama.py:130-160), in place on the packed projection buffer
  * qkv[B*S, row_stride]; the first n_rot heads (q then k) are rotated; cos/sin bf16 [cos_batch, S, D]. */
 int b200_rope(void* qkv, const void* cos_t, const void* sin_t, int B, int S, int n_rot, int D, int row_stride,

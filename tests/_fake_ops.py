@@ -75,6 +75,13 @@ def rmsnorm_bwd(dy, x, weight, rstd, gemma=False):
     return dx.to(x.dtype).view(x.shape), dw.to(weight.dtype)
 
 
+def rope_table(inv_freq, position_ids, attention_scaling=1.0, dtype=torch.bfloat16):
+    ang = position_ids.to(torch.float32)[:, :, None] * inv_freq.to(torch.float32)[None, None, :]
+    emb = torch.cat([ang, ang], dim=-1)
+    _log("rope_table", position_ids)
+    return (emb.cos() * attention_scaling).to(dtype), (emb.sin() * attention_scaling).to(dtype)
+
+
 def rope_(qkv, cos, sin, n_rot_heads, head_dim, backward=False):
     B, S, W = qkv.shape
     assert qkv.is_contiguous()
@@ -424,7 +431,7 @@ class FakePeerWorkspace:
         pass
 
 
-_NAMES = ["gemm", "embedding_fwd", "embedding_bwd", "rmsnorm_fwd", "rmsnorm_bwd", "rope_", "glu_fwd", "glu_bwd", "attn_fwd",
+_NAMES = ["gemm", "embedding_fwd", "embedding_bwd", "rmsnorm_fwd", "rmsnorm_bwd", "rope_", "rope_table", "glu_fwd", "glu_bwd", "attn_fwd",
           "attn_bwd", "ce_fwd", "ce_bwd", "ce_row_lse", "ce_bwd_sharded", "add", "kv_append", "pull_reduce", "gemm_scatter", "moe_route", "moe_gather",
           "moe_combine", "moe_experts_forward", "optim_chunk_elems",
           "adamw_step", "grad_norm", "grad_scale_"]

@@ -29,6 +29,7 @@ SIGNATURES = {
     "b200_rmsnorm_bwd_workspace_rows": [],
     "b200_rmsnorm_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "b200_rope": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    "b200_rope_table": [_p, _p, _p, _p, _i, _i, _f, _p],
     "b200_glu_fwd": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
     "b200_glu_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "b200_add_bf16": [_p, _p, _p, _l, _p],

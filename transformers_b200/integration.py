@@ -152,6 +152,7 @@ def _build_class_map() -> dict:
             "GemmaRMSNorm": mk(g1.GemmaRMSNorm, M.B200RMSNormMixin, _b200_gemma=True),
             "GemmaMLP": mk(g1.GemmaMLP, M.B200MLPMixin),
             "GemmaAttention": mk(g1.GemmaAttention, M.B200AttentionMixin),
+            "GemmaRotaryEmbedding": mk(g1.GemmaRotaryEmbedding, M.B200RotaryEmbeddingMixin),
         }
     except ImportError:  # pragma: no cover
         pass
@@ -160,6 +161,10 @@ def _build_class_map() -> dict:
         "LlamaRMSNorm": mk(ll.LlamaRMSNorm, M.B200RMSNormMixin),
         "LlamaMLP": mk(ll.LlamaMLP, M.B200MLPMixin),
         "LlamaAttention": mk(ll.LlamaAttention, M.B200AttentionMixin),
+        "LlamaRotaryEmbedding": mk(ll.LlamaRotaryEmbedding, M.B200RotaryEmbeddingMixin),
+        "MistralRotaryEmbedding": mk(mi.MistralRotaryEmbedding, M.B200RotaryEmbeddingMixin),
+        "MixtralRotaryEmbedding": mk(mx.MixtralRotaryEmbedding, M.B200RotaryEmbeddingMixin),
+        "Gemma2RotaryEmbedding": mk(g2.Gemma2RotaryEmbedding, M.B200RotaryEmbeddingMixin),
         "MistralRMSNorm": mk(mi.MistralRMSNorm, M.B200RMSNormMixin),
         "MistralMLP": mk(mi.MistralMLP, M.B200MLPMixin),
         "MistralAttention": mk(mi.MistralAttention, M.B200AttentionMixin),

@@ -214,6 +214,36 @@ class B200RMSNormMixin:
         return Fn.RMSNormFn.apply(hidden_states, _local(self.weight), eps, self._b200_gemma)
 
 
+_ROPE_FWD = None
+
+
+def _rope_forward():
+    """The kernel-path body of the rotary module's forward, wrapped like the reference's own (no_grad + dynamic_rope_update,
+    which re-derives ``inv_freq`` for the dynamic / longrope types before the tables are computed:
+    modeling_rope_utils.py)."""
+    global _ROPE_FWD
+    if _ROPE_FWD is None:
+        from transformers.modeling_rope_utils import dynamic_rope_update
+
+        from . import ops
+
+        @torch.no_grad()
+        @dynamic_rope_update
+        def fwd(self, x, position_ids):
+            return ops.rope_table(self.inv_freq, position_ids, float(self.attention_scaling), x.dtype)
+
+        _ROPE_FWD = fwd
+    return _ROPE_FWD
+
+
+class B200RotaryEmbeddingMixin:
+    def forward(self, x, position_ids, *args, **kwargs):  # LlamaRotaryEmbedding.forward models/llama/modeling_llama.py:113-127
+        if (args or kwargs or not _on_b200(x) or x.dtype not in KERNEL_DTYPES or position_ids.dim() != 2
+                or not _on_b200(self.inv_freq)):
+            return super().forward(x, position_ids, *args, **kwargs)
+        return _rope_forward()(self, x, position_ids)
+
+
 class B200MLPMixin:
     def forward(self, x):  # LlamaMLP.forward models/llama/modeling_llama.py:174-176
         if not _on_b200(x):

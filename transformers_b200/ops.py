@@ -154,6 +154,25 @@ def rmsnorm_bwd(dy: torch.Tensor, x: torch.Tensor, weight: torch.Tensor, rstd: t
 
 
 # ----------------------------------------------------------------------------------------------------------- RoPE
+def rope_table(inv_freq: torch.Tensor, position_ids: torch.Tensor, attention_scaling: float = 1.0, dtype: torch.dtype = BF16):
+    """inv_freq fp32 [D/2], position_ids [B, S] (any integer dtype) -> (cos, sin) bf16 [B, S, D]
+    (LlamaRotaryEmbedding.forward, models/llama/modeling_llama.py:113-127)."""
+    lib = _lib_ready()
+    if dtype != BF16:
+        raise B200Error(f"rope_table: only bfloat16 tables are produced, got {dtype}")
+    if not inv_freq.is_cuda or position_ids.device != inv_freq.device:
+        raise B200Error(f"rope_table: expected CUDA tensors on one device, got {inv_freq.device} / {position_ids.device}")
+    f = inv_freq.detach().to(torch.float32).contiguous()
+    pos = position_ids.to(torch.int64).contiguous()
+    B, S = pos.shape
+    D = 2 * f.numel()
+    cos = torch.empty(B, S, D, device=f.device, dtype=BF16)
+    sin = torch.empty(B, S, D, device=f.device, dtype=BF16)
+    check(lib.b200_rope_table(f.data_ptr(), pos.data_ptr(), cos.data_ptr(), sin.data_ptr(), B * S, D, float(attention_scaling),
+                              _stream()), "b200_rope_table")
+    return cos, sin
+
+
 def rope_(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, n_rot_heads: int, head_dim: int, backward: bool = False):
     """In place on qkv [B, S, W] (heads packed along W, the first ``n_rot_heads`` are rotated)."""
     lib = _lib_ready()
