@@ -63,18 +63,21 @@ def parse():
     ap.add_argument("--seq", type=int, default=4096)
     ap.add_argument("--layers", type=int, default=32, help="debug only: fewer layers makes the number INVALID")
     ap.add_argument("--parallelism", default=None, choices=[None, "dp", "tp"])
-    ap.add_argument("--sequence-parallel", type=int, default=int(os.environ.get("B200_TP_SP", "0")),
+    ap.add_argument("--sequence-parallel", type=int, default=1,
                     help="tp only: token-shard the residual stream between the blocks (all-gather / reduce-scatter instead of "
                          "all-reduce), N = chunks the collectives are pipelined in; 0 = plain tp_plan all-reduce")
-    ap.add_argument("--vocab-parallel-loss", type=int, default=int(os.environ.get("B200_TP_VOCAB_LOSS", "0")),
+    ap.add_argument("--vocab-parallel-loss", type=int, default=1,
                     help="tp only: keep lm_head's output vocabulary-sharded and exchange per-row loss statistics instead of "
                          "all-gathering the logits")
-    ap.add_argument("--tp-transport", default=os.environ.get("B200_TP_TRANSPORT", "nccl"), choices=["nccl", "peer", "peer-scatter"],
+    ap.add_argument("--tp-transport", default="peer-scatter", choices=["nccl", "peer", "peer-scatter"],
                     help="tp + sequence-parallel only: 'peer' runs the all-gathers / reduce-scatters with our own kernels and "
                          "copy-engine pulls over NVLink peer memory (symmetric allocations) instead of NCCL; 'peer-scatter' additionally lets the rowwise GEMM's epilogue store every tile "
                          "into its owner's buffer (GEMM + transfer in one kernel)")
-    ap.add_argument("--fuse-residual", type=int, default=int(os.environ.get("B200_FUSE_RESIDUAL", "0")),
-                    help="decoder layers run their residual adds on our kernels (first one fused with the post-attention RMSNorm)")
+    ap.add_argument("--fuse-residual", type=int, default=1,
+                    help="decoder layers run their residual adds on our kernels (first one fused with the post-attention RMSNorm); "
+                         "0 = the reference's torch.add")
+    ap.add_argument("--gemm-tuning", default=None,
+                    help="sweep knob: 'group_m,sync_min_k_nt,sync_min_k_nn,sync_min_k_tt' passed to b200_gemm_tuning")
     ap.add_argument("--pack-weights", type=int, default=int(os.environ.get("B200_PACK_WEIGHTS", "0")),
                     help="make q/k/v and gate/up weights row views of one buffer (no second fused copy in HBM)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -358,7 +361,10 @@ class TimedLib:
             rc = fn(*a)
             e1.record()
             tag = name
-            if name.startswith("b200_gemm"):
+            if name == "b200_gemm_bf16_scatter":  # (A, B, dest, world, rank, M, N, K, lda, ldb, ldc, a_mn, b_mn, stream)
+                tag = f"gemm+scatter[{'T' if a[11] else 'N'}{'T' if a[12] else 'N'}]"
+                self.records.append((tag, e0, e1, 2.0 * a[5] * a[6] * a[7]))
+            elif name.startswith("b200_gemm_bf16"):
                 tag = f"gemm[{'T' if a[9] else 'N'}{'T' if a[10] else 'N'}]"
                 self.records.append((tag, e0, e1, 2.0 * a[3] * a[4] * a[5]))
             else:
@@ -398,6 +404,8 @@ def run_b200(args):
     from transformers_b200 import _lib, ops
 
     transformers_b200.enable()
+    if args.gemm_tuning:
+        ops.gemm_tuning(*[int(v) for v in args.gemm_tuning.split(",")])
     cfg_kw = dict(LLAMA3_8B)
     cfg_kw["num_hidden_layers"] = args.layers
     cfg_kw["use_cache"] = False  # training step: no KV cache (as Trainer does under gradient checkpointing / fwd+bwd only)
@@ -414,6 +422,7 @@ def run_b200(args):
         if args.tp_transport != "nccl":
             if args.sequence_parallel <= 0:
                 raise SystemExit("--tp-transport peer / peer-scatter needs --sequence-parallel 1")
+            args.sequence_parallel = 1  # the peer transport uses one row block per rank
             from transformers_b200.symm import PeerWorkspace
 
             peer_ws = PeerWorkspace(dist.group.WORLD, scatter_epilogue=args.tp_transport == "peer-scatter")
@@ -528,6 +537,11 @@ def run_b200(args):
                          "whole_step_frac": per_gpu_tf / peak_tf},
             "kernels_ms": {k: {"ms": round(v[0], 3), "launches": v[1]} for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])},
         }
+        if world > 1:
+            # what the step spends outside this rank's own kernels: collectives / barriers / copy-engine gathers that are
+            # not hidden under compute, plus host gaps (the instrumented step's kernel times are device-event durations)
+            line["comm"] = {"exposed_ms_per_step": round(ms_step - ours_ms, 2), "kernels_ms_per_step": round(ours_ms, 2),
+                            "note": "ms_per_step minus the summed durations of this rank's kernels in one instrumented step (rank 0)"}
         if not args.no_cpu_baseline and world == 1:
             try:
                 line["cpu_baseline"] = cpu_baseline_block()

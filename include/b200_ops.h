@@ -28,14 +28,19 @@ const char* b200_last_error(void);     /* thread-local message of the last faili
 int b200_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
                    int b_mn, int accumulate, b200_stream_t stream);
 /* decode rows, 1 <= M <= 4: y[M,N] = x[M,K] W[N,K]^T as one stream over W (HBM-bound: CUDA cores, one warp per output
- * column); b200_gemm_bf16 dispatches to it for such shapes when B200_GEMV=1 */
+ * column); b200_gemm_bf16 dispatches to it for such shapes */
 int b200_gemv_bf16(const void* x, const void* W, void* y, int M, int N, int K, int ldx, int ldw, int ldy,
                    b200_stream_t stream);
 /* CTA-pair variant (tcgen05 cta_group::2, 256x256 tile per 2-CTA cluster); b200_gemm_bf16 dispatches to it for M > 128 */
 int b200_gemm_bf16_2sm(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
                        int b_mn, int accumulate, b200_stream_t stream);
-int b200_gemm_bf16_ex(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
-                      int b_mn, int accumulate, int desc_variant, b200_stream_t stream);
+/* tuning knobs of the CTA-pair kernel for sweeps (process-wide; defaults are the measured optimum): M tiles per
+ * rasterisation group (0 = unchanged) and, per layout (NT fwd / NN dgrad / TT wgrad), the smallest K from which the
+ * lock-step variant runs (0 = never, < 0 = unchanged) */
+int b200_gemm_tuning(int group_m, int sync_min_k_nt, int sync_min_k_nn, int sync_min_k_tt);
+/* 1-CTA variant (128x256 tiles); b200_gemm_bf16 dispatches to it for M <= 128 */
+int b200_gemm_bf16_1sm(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
+                       int b_mn, int accumulate, b200_stream_t stream);
 
 /* nn.Embedding gather / scatter-add (models/llama/modeling_llama.py:353,381; scaled variant
  * models/gemma2/modeling_gemma2.py:338-349).  ids int64[T]; err_flag int32[1] set to 1 on out-of-range ids. */
@@ -86,9 +91,6 @@ int b200_attn_bwd(const void* q, const void* k, const void* v, const void* out, 
                   void* dq, void* dk, void* dv, float* workspace, int B, int Sq, int Skv, int Hq, int Hkv, int D,
                   int lse_stride, const int64_t* strides, float scale, float softcap, int causal, int window,
                   const int* kv_start, const int* kv_end, b200_stream_t stream);
-
-/* bring-up aid: int64[16] device buffer filled with per-role cycle counters by CTA 0 of the dK/dV kernel; NULL = off */
-int b200_debug_set_buffer(void* device_i64_buffer);
 
 /* In-place KV-cache append replacing torch.cat in DynamicLayer.update (cache_utils.py:127-146; Cache.update :1349-1381):
  * writes rows [offset, offset+q_len) of the preallocated [B,H,capacity,D] caches. */

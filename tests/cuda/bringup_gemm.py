@@ -25,8 +25,8 @@ def run(M, N, K, a_mn, b_mn, variant, accumulate=0, seed=0):
         rc = lib.b200_gemm_bf16_2sm(As.data_ptr(), Bs.data_ptr(), C.data_ptr(), M, N, K, As.stride(0), Bs.stride(0), C.stride(0),
                                     a_mn, b_mn, accumulate, torch.cuda.current_stream().cuda_stream)
     else:
-        rc = lib.b200_gemm_bf16_ex(As.data_ptr(), Bs.data_ptr(), C.data_ptr(), M, N, K, As.stride(0), Bs.stride(0), C.stride(0),
-                                   a_mn, b_mn, accumulate, variant, torch.cuda.current_stream().cuda_stream)
+        rc = lib.b200_gemm_bf16_1sm(As.data_ptr(), Bs.data_ptr(), C.data_ptr(), M, N, K, As.stride(0), Bs.stride(0), C.stride(0),
+                                    a_mn, b_mn, accumulate, torch.cuda.current_stream().cuda_stream)
     if rc != 0:
         return f"rc={rc} {_lib.last_error()}"
     torch.cuda.synchronize()
@@ -55,7 +55,7 @@ def bench(M, N, K, a_mn, b_mn, iters=20):
     C = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
     st = torch.cuda.current_stream().cuda_stream
     f = lambda: lib.b200_gemm_bf16_2sm(A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, K, A.stride(0), B.stride(0), C.stride(0), a_mn, b_mn, 0, st)
-    f1 = lambda: lib.b200_gemm_bf16_ex(A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, K, A.stride(0), B.stride(0), C.stride(0), a_mn, b_mn, 0, 0, st)
+    f1 = lambda: lib.b200_gemm_bf16_1sm(A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, K, A.stride(0), B.stride(0), C.stride(0), a_mn, b_mn, 0, st)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(3): f1()
     torch.cuda.synchronize(); e0.record()

@@ -1,6 +1,6 @@
 """The ALGORITHM of csrc/attention_decode.cu restated in torch on CPU (same split ranges, same per-(warp, row-group) online
 softmax in the exp2 domain, same two-level merge through (m, l, O) triples) against a plain fp32 softmax.  This cannot
-check the CUDA mechanics (that is tests/test_experimental_gpu.py on a device); it pins the index arithmetic and the merge
+check the CUDA mechanics (that is tests/test_kernels2_gpu.py on a device); it pins the index arithmetic and the merge
 formulas the kernel implements, including empty splits, padding ranges, the sliding window and the softcap."""
 import math
 

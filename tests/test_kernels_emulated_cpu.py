@@ -2,7 +2,7 @@
 HOST by tests/emu (one std::thread per CUDA thread, real warp-shuffle and barrier semantics): the kernels' own source is
 compiled with g++ and checked against torch.  This pins indexing, vector/tail paths, shuffle reductions and shared-memory
 merges before the first device run; device-only aspects (coalescing, latency, the launchers) are left to
-tests/test_experimental_gpu.py."""
+tests/test_kernels2_gpu.py."""
 import ctypes
 import math
 import os

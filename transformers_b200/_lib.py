@@ -22,7 +22,8 @@ SIGNATURES = {
     "b200_gemm_bf16": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "b200_gemv_bf16": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "b200_gemm_bf16_2sm": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
-    "b200_gemm_bf16_ex": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "b200_gemm_tuning": [_i, _i, _i, _i],
+    "b200_gemm_bf16_1sm": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "b200_embedding_fwd": [_p, _p, _p, _i, _i, _i, _f, _i, _p, _p],
     "b200_embedding_bwd": [_p, _p, _p, _i, _i, _i, _l, _f, _i, _p],
     "b200_rmsnorm_fwd": [_p, _p, _p, _p, _p, _p, _i, _i, _f, _i, _p],
@@ -33,7 +34,6 @@ SIGNATURES = {
     "b200_glu_fwd": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
     "b200_glu_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "b200_add_bf16": [_p, _p, _p, _l, _p],
-    "b200_debug_set_buffer": [_p],
     "b200_kv_append": [_p, _p, _p, _p, _i, _i, _i, _i] + [_l] * 9 + [_i, _i, _p],
     "b200_moe_route": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "b200_moe_gather": [_p, _p, _p, _i, _i, _p],

@@ -208,10 +208,10 @@ def layer_class():
     return _LAYER_CLS
 
 
-def make_cache(config, inplace_sliding: bool = False):
-    """DynamicCache(config=...) (cache_utils.py:1773-1815) with every full-attention layer replaced by B200DynamicLayer;
-    sliding-window layers keep the reference's DynamicSlidingWindowLayer unless ``inplace_sliding`` (B200SlidingWindowLayer:
-    same semantics, no per-token copy of the window; written after round 1's GPU budget, CPU-validated only)."""
+def make_cache(config, inplace_sliding: bool = True):
+    """DynamicCache(config=...) (cache_utils.py:1773-1815) with every full-attention layer replaced by B200DynamicLayer and
+    every sliding-window layer by B200SlidingWindowLayer (same semantics as DynamicSlidingWindowLayer without the per-token
+    copy of the window; ``inplace_sliding=False`` keeps the reference layer type for those)."""
     from transformers.cache_utils import DynamicCache, DynamicLayer, DynamicSlidingWindowLayer
 
     cache = DynamicCache(config=config)

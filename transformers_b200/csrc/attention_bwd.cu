@@ -30,18 +30,7 @@ struct AttnBwdParams {
   __nv_bfloat16* dk;
   __nv_bfloat16* dv;
   int64_t dq_bs, dq_rs, dq_hs, dk_bs, dk_rs, dk_hs, dv_bs, dv_rs, dv_hs;
-  long long* dbg;  // optional cycle counters of CTA 0 (b200_debug_set_buffer); NULL in production
 };
-
-static long long* g_dbg_buffer = nullptr;
-#define DBG_ON (p.dbg != nullptr && blockIdx.x == 0)
-#define DBG_T0() long long _t0 = DBG_ON ? clock64() : 0
-#define DBG_ACC(var) \
-  if (DBG_ON) {       \
-    long long _t1 = clock64(); \
-    var += _t1 - _t0; \
-    _t0 = _t1;        \
-  }
 
 // ------------------------------------------------------------------------------------------------ preprocess
 __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
@@ -165,14 +154,11 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tma_load_4d(sK + c * KV_CHUNK, &tmK, kv_full, c * 64, kv0, hkv, b);
         tma_load_4d(sV + c * KV_CHUNK, &tmV, kv_full, c * 64, kv0, hkv, b);
       }
-      long long w_empty = 0, t_total = DBG_ON ? clock64() : 0;
       for (int it = 0; it < n_iter; ++it) {
         const int st = it % NST;
         const int hq = hkv * n_rep + it / n_qt;
         const int q0 = (qt_lo + it % n_qt) * Q_TILE;
-        DBG_T0();
         mbar_wait(&q_empty[st], ((it / NST) & 1) ^ 1);
-        DBG_ACC(w_empty);
         mbar_expect_tx(&q_full[st], 2 * Q_BYTES + 2 * Q_TILE * 4);
 #pragma unroll
         for (int c = 0; c < DCH; ++c) {
@@ -183,11 +169,6 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         bulk_load_1d(sLse + st * Q_TILE, p.lse2 + row_base, Q_TILE * 4, &q_full[st]);
         bulk_load_1d(sDelta + st * Q_TILE, p.delta + row_base, Q_TILE * 4, &q_full[st]);
       }
-      if (DBG_ON) {
-        p.dbg[0] = clock64() - t_total;
-        p.dbg[1] = w_empty;
-        p.dbg[2] = n_iter;
-      }
     }
   } else if (warp == BWD_MMA_WARP) {
     if (n_iter > 0 && elect_one()) {
@@ -197,13 +178,10 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const uint64_t dK_k = make_smem_desc(smem_u32(sK), 16, 1024, SWZ_128B), dV_k = make_smem_desc(smem_u32(sV), 16, 1024, SWZ_128B);
       const uint64_t dQ_k = make_smem_desc(smem_u32(sQ), 16, 1024, SWZ_128B), ddO_k = make_smem_desc(smem_u32(sdO), 16, 1024, SWZ_128B);
       const uint64_t dQ_mn = make_smem_desc(smem_u32(sQ), Q_CHUNK, 1024, SWZ_128B), ddO_mn = make_smem_desc(smem_u32(sdO), Q_CHUNK, 1024, SWZ_128B);
-      long long w_qfull = 0, w_pds = 0, t_issue = 0, t_issue2 = 0, t_total = DBG_ON ? clock64() : 0;
       auto issue_sdp = [&](int it) {
         const int buf = it & 1;
         const int st = it % NST;
-        DBG_T0();
         mbar_wait(&q_full[st], (it / NST) & 1);
-        DBG_ACC(w_qfull);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
@@ -218,7 +196,6 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           umma_ss(tmem_base + DP_COL + buf * 64, desc_advance(dV_k, oa), desc_advance(ddO_k, ob), idesc_s, kk != 0);
         }
         umma_commit(&sdp_full[buf]);
-        DBG_ACC(t_issue);
       };
       mbar_wait(kv_full, 0);
       issue_sdp(0);
@@ -226,9 +203,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const int buf = it & 1;
         const int st = it % NST;
         if (it + 1 < n_iter) issue_sdp(it + 1);
-        DBG_T0();
         mbar_wait(&pds_full[buf], (it >> 1) & 1);
-        DBG_ACC(w_pds);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < Q_TILE / 16; ++kk) {
@@ -242,16 +217,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                   desc_advance(dQ_mn, st * Q_BYTES + kk * 2048), idesc_acc, (it | kk) != 0);
         }
         umma_commit(&q_empty[st]);
-        DBG_ACC(t_issue2);
       }
       umma_commit(acc_full);
-      if (DBG_ON) {
-        p.dbg[4] = clock64() - t_total;
-        p.dbg[5] = w_qfull;
-        p.dbg[6] = w_pds;
-        p.dbg[7] = t_issue;
-        p.dbg[11] = t_issue2;
-      }
     }
   } else {
     const int qd = warp & 3;    // TMEM lane quarter: hardware lets warp w touch lanes 32*(w%4).. only
@@ -642,12 +609,6 @@ static int launch_bwd(const CUtensorMap& tq64, const CUtensorMap& tk128, const C
 
 }  // namespace b200
 
-// Debug: device buffer of >= 16 int64 that CTA 0 of the dK/dV kernel fills with per-role cycle counters (NULL = off).
-extern "C" int b200_debug_set_buffer(void* device_i64_buffer) {
-  b200::g_dbg_buffer = reinterpret_cast<long long*>(device_i64_buffer);
-  return 0;
-}
-
 // Workspace: fp32 [2 * B * Hq * lse_stride] (delta, lse2).  lse is the forward's output with the same lse_stride
 // (a multiple of 128 and >= Sq).  All tensors are strided [B, S, h, D] views (strides in elements).
 extern "C" int b200_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout,
@@ -710,7 +671,6 @@ extern "C" int b200_attn_bwd(const void* q, const void* k, const void* v, const 
   p.dq_bs = sdq[0]; p.dq_rs = sdq[1]; p.dq_hs = sdq[2];
   p.dk_bs = sdk[0]; p.dk_rs = sdk[1]; p.dk_hs = sdk[2];
   p.dv_bs = sdv[0]; p.dv_rs = sdv[1]; p.dv_hs = sdv[2];
-  p.dbg = g_dbg_buffer;
   const bool sc = softcap > 0.f;
   if (D == 128)
     return sc ? launch_bwd<128, true>(tq64, tk128, tv128, tdo64, tq128, tk64, tv64, tdo128, p, stream)

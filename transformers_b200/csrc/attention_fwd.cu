@@ -371,16 +371,12 @@ static int launch_attn_fwd_v(const CUtensorMap& tq, const CUtensorMap& tk, const
   return B200_OK;
 }
 
-// B200_ATTN_FWD_ILP=1 selects the softmax variant with batched TMEM loads and split max / sum chains (written after the
-// round-1 GPU budget was spent: same math, different instruction schedule; to be measured before it becomes the default)
 template <int D, bool SOFTCAP>
 static int launch_attn_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnFwdParams& p,
                            cudaStream_t stream) {
-  static const bool ilp = [] {
-    const char* e = getenv("B200_ATTN_FWD_ILP");
-    return e && atoi(e) > 0;
-  }();
-  return ilp ? launch_attn_fwd_v<D, SOFTCAP, true>(tq, tk, tv, p, stream) : launch_attn_fwd_v<D, SOFTCAP, false>(tq, tk, tv, p, stream);
+  // softmax stage with batched TMEM loads and split max / sum dependency chains (measured 0.578 vs 0.587 ms for the
+  // one-chain variant at B4 S4096 32/8 heads, profiles/r02_call1_validation.md); the one-chain variant is gone
+  return launch_attn_fwd_v<D, SOFTCAP, true>(tq, tk, tv, p, stream);
 }
 
 }  // namespace b200

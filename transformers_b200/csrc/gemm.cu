@@ -247,9 +247,9 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 }  // namespace b200
 
 // C-ABI.  a_mn / b_mn: 0 = operand stored [rows = M or N, cols = K] (K-major); 1 = stored [rows = K, cols = M or N].
-// lda / ldb / ldc are row strides in elements.  desc_variant (debug): 0 = default smem-descriptor offsets.
-extern "C" int b200_gemm_bf16_ex(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
-                                 int a_mn, int b_mn, int accumulate, int desc_variant, cudaStream_t stream) {
+// lda / ldb / ldc are row strides in elements.  1-CTA kernel (128 x 256 tiles): used for M <= 128 (one tile tall).
+extern "C" int b200_gemm_bf16_1sm(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
+                                  int a_mn, int b_mn, int accumulate, cudaStream_t stream) {
   using namespace b200;
   B200_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   B200_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % 8 == 0, "gemm: C must be 16B aligned, ldc %% 8 == 0");
@@ -282,10 +282,6 @@ extern "C" int b200_gemm_bf16_ex(const void* A, const void* B, void* C, int M, i
   p.a_sbo = a_mn ? mn_sbo : k_sbo;
   p.b_lbo = b_mn ? mn_lbo : k_lbo;
   p.b_sbo = b_mn ? mn_sbo : k_sbo;
-  if (desc_variant == 1) {  // swapped roles of LBO / SBO for MN-major operands (bring-up probe)
-    if (a_mn) { p.a_lbo = mn_sbo; p.a_sbo = mn_lbo; }
-    if (b_mn) { p.b_lbo = mn_sbo; p.b_sbo = mn_lbo; }
-  }
   if (!a_mn && !b_mn) return launch_gemm<0, 0>(tmA, tmB, p, stream);
   if (!a_mn && b_mn) return launch_gemm<0, 1>(tmA, tmB, p, stream);
   if (a_mn && b_mn) return launch_gemm<1, 1>(tmA, tmB, p, stream);
@@ -297,26 +293,18 @@ extern "C" int b200_gemm_bf16_2sm(const void* A, const void* B, void* C, int M, 
 
 // Dispatcher.  Measured on the full Llama-3-8B step under the 1 kW power cap (profiles/README.md): the CTA-pair kernel
 // (gemm2.cu, 256x256 tiles, 32 KB/stage/SM) sustains 1453 TF/s vs 1351 TF/s for the 1-CTA 128x256 kernel, so it is the
-// default for anything taller than one tile; B200_GEMM_1SM=1 forces the 1-CTA kernel (A/B timing, tiny shapes use it anyway).
+// default for anything taller than one tile; shapes of one tile or less use the 1-CTA kernel.
 extern "C" int b200_gemv_bf16(const void* x, const void* W, void* y, int M, int N, int K, int ldx, int ldw, int ldy,
                               cudaStream_t stream);
 
 extern "C" int b200_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
                               int a_mn, int b_mn, int accumulate, cudaStream_t stream) {
-  static const int force_1sm = [] {
-    const char* e = getenv("B200_GEMM_1SM");
-    return (e && e[0] == '1') ? 1 : 0;
-  }();
-  // decode rows (M <= 4): stream the weights with the CUDA-core kernel of gemv.cu instead of a mostly empty tensor-core tile
-  // (B200_GEMV=1; written after the round-1 GPU budget was spent -- opt-in until it has run on a device)
-  static const int use_gemv = [] {
-    const char* e = getenv("B200_GEMV");
-    return (e && e[0] == '1') ? 1 : 0;
-  }();
-  if (use_gemv && M >= 1 && M <= 4 && !a_mn && !b_mn && !accumulate && K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 &&
+  // decode rows (M <= 4): stream the weights once with the CUDA-core kernel of gemv.cu (4.2-6.1 TB/s of weight stream
+  // measured) instead of a 1/128-full tensor-core tile
+  if (M >= 1 && M <= 4 && !a_mn && !b_mn && !accumulate && K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 &&
       (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0)
     return b200_gemv_bf16(A, B, C, M, N, K, lda, ldb, ldc, stream);
-  if (!force_1sm && M > 128 && N > 64)
+  if (M > 128 && N > 64)
     return b200_gemm_bf16_2sm(A, B, C, M, N, K, lda, ldb, ldc, a_mn, b_mn, accumulate, stream);
-  return b200_gemm_bf16_ex(A, B, C, M, N, K, lda, ldb, ldc, a_mn, b_mn, accumulate, 0, stream);
+  return b200_gemm_bf16_1sm(A, B, C, M, N, K, lda, ldb, ldc, a_mn, b_mn, accumulate, stream);
 }

@@ -9,7 +9,6 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
-#include <stdlib.h>
 
 namespace b200 {
 
@@ -315,17 +314,15 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   }
 }
 
-// B200_GEMM2_SYNC=1 (K >= B200_GEMM2_SYNC_MIN_K, default 8192) selects the lock-step variant.  Written after the round-1 GPU
-// budget was spent: to be measured (ncu dram__bytes, step time) before it becomes the default.  Assumes one device per
-// process and stream-ordered GEMM launches (both true for this package).
-static bool gemm2_sync_wanted(int K) {
-  static const int min_k = [] {
-    const char* on = getenv("B200_GEMM2_SYNC");
-    if (!on || atoi(on) <= 0) return -1;
-    const char* mk = getenv("B200_GEMM2_SYNC_MIN_K");
-    return mk && atoi(mk) > 0 ? atoi(mk) : 8192;
-  }();
-  return min_k > 0 && K >= min_k;
+// Tuning knobs of the CTA-pair GEMM, set through b200_gemm_tuning() (an explicit host call for sweeps; NOT read from the
+// environment): rasterisation group size and, per operand layout, the smallest K from which the lock-step variant runs
+// (0 = never).  Defaults = what measured best on the Llama-3-8B step (profiles/README.md, round 2).
+static int g_group_m = 8;
+static int g_sync_min_k[2][2] = {{0, 0}, {0, 0}};  // [a_mn][b_mn]
+
+static bool gemm2_sync_wanted(int a_mn, int b_mn, int K) {
+  const int mk = g_sync_min_k[a_mn ? 1 : 0][b_mn ? 1 : 0];
+  return mk > 0 && K >= mk;
 }
 
 template <int A_MN, int B_MN, int MODE>
@@ -375,8 +372,8 @@ template <int A_MN, int B_MN>
 static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const Gemm2Params& p,
                         cudaStream_t stream) {
   if (p.scatter_maps) return launch_gemm2_v<A_MN, B_MN, G2_MODE_SCATTER>(tmA, tmB, tmC, p, stream);
-  return gemm2_sync_wanted(p.K) ? launch_gemm2_v<A_MN, B_MN, G2_MODE_SYNC>(tmA, tmB, tmC, p, stream)
-                                : launch_gemm2_v<A_MN, B_MN, G2_MODE_PLAIN>(tmA, tmB, tmC, p, stream);
+  return gemm2_sync_wanted(A_MN, B_MN, p.K) ? launch_gemm2_v<A_MN, B_MN, G2_MODE_SYNC>(tmA, tmB, tmC, p, stream)
+                                            : launch_gemm2_v<A_MN, B_MN, G2_MODE_PLAIN>(tmA, tmB, tmC, p, stream);
 }
 
 }  // namespace b200
@@ -417,14 +414,7 @@ static int gemm2_run(const void* A, const void* B, void* C, int M, int N, int K,
   p.scatter_maps = scatter_maps;
   p.rows_per_owner = rows_per_owner;
   p.m_rot = m_rot;
-  // M tiles per rasterisation group (wave footprint ~ group_m x 74/group_m tiles of 256x256).  B200_GEMM2_GROUP_M overrides the
-  // default for sweeps (profiles/README.md: DRAM re-reads are the open issue of this kernel).
-  static const int group_m_env = [] {
-    const char* e = getenv("B200_GEMM2_GROUP_M");
-    const int v = e ? atoi(e) : 0;
-    return v > 0 && v <= 64 ? v : 8;
-  }();
-  p.group_m = group_m_env;
+  p.group_m = b200::g_group_m;  // M tiles per rasterisation group (wave footprint ~ group_m x 74/group_m tiles of 256x256)
   const uint32_t k_lbo = 16, k_sbo = 1024, mn_lbo = 64 * G2_BK * 2, mn_sbo = 1024;
   p.a_lbo = a_mn ? mn_lbo : k_lbo;
   p.a_sbo = a_mn ? mn_sbo : k_sbo;
@@ -434,6 +424,18 @@ static int gemm2_run(const void* A, const void* B, void* C, int M, int N, int K,
   if (!a_mn && b_mn) return launch_gemm2<0, 1>(tmA, tmB, tmC, p, stream);
   if (a_mn && b_mn) return launch_gemm2<1, 1>(tmA, tmB, tmC, p, stream);
   return launch_gemm2<1, 0>(tmA, tmB, tmC, p, stream);
+}
+
+// group_m: M tiles per rasterisation group (1..64; 0 = leave unchanged).  sync_min_k_*: smallest K from which the
+// lock-step variant is used for that layout (NT = forward, NN = dgrad, TT = wgrad); 0 = never, < 0 = leave unchanged.
+// Process-wide; intended for sweeps (tests/cuda) -- the defaults are the measured optimum.
+extern "C" int b200_gemm_tuning(int group_m, int sync_min_k_nt, int sync_min_k_nn, int sync_min_k_tt) {
+  B200_REQUIRE(group_m >= 0 && group_m <= 64, "gemm_tuning: group_m %d outside 0..64", group_m);
+  if (group_m > 0) b200::g_group_m = group_m;
+  if (sync_min_k_nt >= 0) b200::g_sync_min_k[0][0] = sync_min_k_nt;
+  if (sync_min_k_nn >= 0) b200::g_sync_min_k[0][1] = sync_min_k_nn;
+  if (sync_min_k_tt >= 0) b200::g_sync_min_k[1][1] = sync_min_k_tt;
+  return B200_OK;
 }
 
 // Same contract as b200_gemm_bf16 (gemm.cu); requires M > 128 to be worthwhile.  Called by the dispatcher there.

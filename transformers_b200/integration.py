@@ -217,11 +217,11 @@ def b200_causal_lm_loss(logits, labels, vocab_size=None, num_items_in_batch=None
 
 
 def accelerate(model: nn.Module, attn: bool = True, head_and_loss: bool = True, pack_weights: bool = False,
-               fuse_residual: bool = False) -> nn.Module:
+               fuse_residual: bool = True) -> nn.Module:
     """Convert an already constructed reference model in place (class swap, parameters untouched).
     ``pack_weights``: additionally make q/k/v and gate/up weights row views of one buffer (modules.pack_weights).
-    ``fuse_residual``: Llama / Mistral decoder layers run their residual adds on our kernels, the first fused with the
-    post-attention RMSNorm (modules.B200DecoderLayerMixin; CPU-validated, GPU run pending)."""
+    ``fuse_residual`` (default): Llama / Mistral decoder layers run their residual adds on our kernels, the first fused
+    with the post-attention RMSNorm (modules.B200DecoderLayerMixin); False keeps the reference's ``torch.add``."""
     enable()
     cmap = _class_map()
     by_base = {cls.__mro__[2]: cls for cls in cmap.values()}  # (B200X, mixin, base, ...)

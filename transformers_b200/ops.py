@@ -81,6 +81,11 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     return out
 
 
+def gemm_tuning(group_m: int = 0, sync_min_k_nt: int = -1, sync_min_k_nn: int = -1, sync_min_k_tt: int = -1) -> None:
+    """Sweep knobs of the CTA-pair GEMM (include/b200_ops.h: b200_gemm_tuning); process-wide."""
+    _check(_lib.load().b200_gemm_tuning(int(group_m), int(sync_min_k_nt), int(sync_min_k_nn), int(sync_min_k_tt)), "b200_gemm_tuning")
+
+
 # ------------------------------------------------------------------------------------------------------ embedding
 def embedding_fwd(ids: torch.Tensor, weight: torch.Tensor, scale: float | None = None) -> torch.Tensor:
     lib = _lib_ready()
@@ -236,18 +241,14 @@ def _bsh_strides(t: torch.Tensor):
     return t.stride(0), t.stride(1), t.stride(2)
 
 
-# B200_DECODE_ATTN=1: route q_len == 1 through the split-context decode kernel (written after round 1's GPU budget was
-# spent; opt-in until it has run on a device)
-_DECODE_ATTN = os.environ.get("B200_DECODE_ATTN", "0") == "1"
-
-
 def _lse_stride(sq: int) -> int:
     return (sq + 127) // 128 * 128
 
 
 def attn_fwd(q, k, v, *, scale: float, causal: bool, window: int = 0, softcap: float = 0.0, kv_start=None, kv_end=None,
-             out: torch.Tensor | None = None):
-    """q [B,Sq,Hq,D], k/v [B,Skv,Hkv,D] strided views -> (out [B,Sq,Hq,D], lse [B,Hq,lse_stride] fp32)."""
+             out: torch.Tensor | None = None, decode_kernel: bool | None = None):
+    """q [B,Sq,Hq,D], k/v [B,Skv,Hkv,D] strided views -> (out [B,Sq,Hq,D], lse [B,Hq,lse_stride] fp32).
+    q_len == 1 goes to the split-context decode kernels (``decode_kernel=False`` forces the tensor-core kernel: tests)."""
     lib = _lib_ready()
     _chk_bf16(q, k, v)
     B, Sq, Hq, D = q.shape
@@ -256,7 +257,7 @@ def attn_fwd(q, k, v, *, scale: float, causal: bool, window: int = 0, softcap: f
         out = torch.empty(B, Sq, Hq, D, device=q.device, dtype=BF16)
     ls = _lse_stride(Sq)
     lse = torch.empty(B, Hq, ls, device=q.device, dtype=torch.float32)
-    if Sq == 1 and _DECODE_ATTN and Hq // Hkv in (1, 2, 4, 8):
+    if Sq == 1 and Hq // Hkv in (1, 2, 4, 8) and decode_kernel is not False:
         # decode step: split-context CUDA-core kernel (attention_decode.cu) instead of a 1/128-full tensor-core q tile
         nsplit = lib.b200_attn_decode_splits(B, Hkv, Skv)
         ws = torch.empty(B * Hq * nsplit * (D + 2), device=q.device, dtype=torch.float32)
