@@ -76,11 +76,14 @@ def parse():
     ap.add_argument("--fuse-residual", type=int, default=1,
                     help="decoder layers run their residual adds on our kernels (first one fused with the post-attention RMSNorm); "
                          "0 = the reference's torch.add")
-    ap.add_argument("--gemm-tuning", default=None,
-                    help="sweep knob: 'group_m,sync_min_k_nt,sync_min_k_nn,sync_min_k_tt' passed to b200_gemm_tuning")
     ap.add_argument("--pack-weights", type=int, default=int(os.environ.get("B200_PACK_WEIGHTS", "0")),
                     help="make q/k/v and gate/up weights row views of one buffer (no second fused copy in HBM)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="llama3-8b-train",
+                    choices=["llama3-8b-train", "llama3-8b-trainer-step", "mixtral-8x7b-forward", "gemma2-9b-generate"],
+                    help="llama3-8b-train = BASELINE.json configs[1]/[2] (the contract's bench line).  The others are secondary "
+                         "lines on one GPU: the Trainer-shaped step (fwd + bwd + fused grad-norm clip + AdamW), configs[3] "
+                         "(Mixtral-8x7B forward, seq 2048) and configs[4] (Gemma-2-9B generate: prefill 8192 + decode 512)")
     return ap.parse_args()
 
 
@@ -404,8 +407,6 @@ def run_b200(args):
     from transformers_b200 import _lib, ops
 
     transformers_b200.enable()
-    if args.gemm_tuning:
-        ops.gemm_tuning(*[int(v) for v in args.gemm_tuning.split(",")])
     cfg_kw = dict(LLAMA3_8B)
     cfg_kw["num_hidden_layers"] = args.layers
     cfg_kw["use_cache"] = False  # training step: no KV cache (as Trainer does under gradient checkpointing / fwd+bwd only)
@@ -552,10 +553,211 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------ secondary configs
+MIXTRAL_8X7B = dict(vocab_size=32000, hidden_size=4096, intermediate_size=14336, num_hidden_layers=32, num_attention_heads=32,
+                    num_key_value_heads=8, head_dim=128, num_local_experts=8, num_experts_per_tok=2,
+                    max_position_embeddings=32768, sliding_window=None, rms_norm_eps=1e-5, use_cache=False,
+                    rope_parameters={"rope_type": "default", "rope_theta": 1000000.0})
+GEMMA2_9B = dict(vocab_size=256000, hidden_size=3584, intermediate_size=14336, num_hidden_layers=42, num_attention_heads=16,
+                 num_key_value_heads=8, head_dim=256, sliding_window=4096, query_pre_attn_scalar=256,
+                 attn_logit_softcapping=50.0, final_logit_softcapping=30.0, max_position_embeddings=16384,
+                 rope_parameters={"rope_type": "default", "rope_theta": 10000.0})
+
+
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def _event_ms(fn, iters):
+    import torch
+
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters, out
+
+
+def run_secondary(args):
+    """One JSON line for a secondary config on ONE GPU (same keys as the main line; not the contract's bench value)."""
+    import torch
+
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise SystemExit(f"--config {args.config} is a single-GPU line")
+    torch.cuda.set_device(0)
+    tf = import_transformers()
+    import transformers_b200
+    from transformers_b200 import ops
+
+    transformers_b200.enable()
+    peaks = _peaks()
+    peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
+    peak_bw = peaks.get("hbm_gbs") or 6500.0
+    BF = torch.bfloat16
+    sampler = ClockSampler(0)
+    steps, warmup = args.steps, max(args.warmup, 3)
+    base = {"n_gpus": 1, "steps": steps, "warmup": warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic"}
+    if args.config == "mixtral-8x7b-forward":
+        cfg = tf.MixtralConfig(**MIXTRAL_8X7B)
+        tf.set_seed(42)
+        with torch.device("cuda"):
+            model = tf.MixtralForCausalLM._from_config(cfg, attn_implementation="b200", dtype=BF)
+        transformers_b200.accelerate(model)
+        model.eval()
+        S = 2048
+        torch.manual_seed(0)
+        ids_host = torch.randint(0, cfg.vocab_size, (1, S), dtype=torch.int64).pin_memory()
+        ids_dev, stage = ids_host.cuda(), torch.empty(1, S, dtype=torch.int64, device="cuda")
+
+        def resident():
+            with torch.no_grad():
+                return model(input_ids=ids_dev).logits
+
+        def e2e():
+            stage.copy_(ids_host, non_blocking=True)
+            with torch.no_grad():
+                return int(model(input_ids=stage).logits[0, -1].argmax())  # device -> host read of the step's result
+
+        for _ in range(warmup):
+            resident()
+        n0 = ops.launch_count()
+        sampler.start()
+        ms, _ = _event_ms(resident, steps)
+        launches = ops.launch_count() - n0
+        ms_e2e, _ = _event_ms(e2e, steps)
+        sampler.stop_flag = True
+        # 2 FLOP per active parameter per token (attention + router + 2 of 8 experts + lm_head) + causal attention
+        flops = (2 * 12.88e9 + 32 * 4 * S * 32 * 128 / 2) * S
+        tfs = flops / (ms * 1e-3) / 1e12
+        line = {**base, "metric": "tokens/sec Mixtral-8x7B forward seq2048", "value": S / (ms * 1e-3), "unit": "tokens/s",
+                "ms_per_step": ms,
+                "config": {"workload": "Mixtral-8x7B bf16 forward seq=2048 batch=1 on 1xB200 (configs[3])",
+                           "model": "Mixtral-8x7B (random init, 46.7 B parameters resident: 93 GB)", "global_batch": 1, "seq_len": S,
+                           "parallelism": "single", "l2": "93 GB of weights >> 126 MB L2; no explicit flush needed"},
+                "e2e": {"value": S / (ms_e2e * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": S * 8, "d2h_bytes_per_step": 8,
+                        "ms_per_step": ms_e2e},
+                "gpu_launches": launches,
+                "roofline": {"bound": "tensor", "kernel": "whole forward (expert / attention / head GEMMs dominate)", "achieved": tfs,
+                             "peak": peak_tf, "unit": "TFLOP/s", "frac": tfs / peak_tf,
+                             "peak_source": "measured sustained (MEASURED_PEAKS.json)" if peaks else "fallback", "traffic": None}}
+    elif args.config == "gemma2-9b-generate":
+        from transformers_b200.cache import make_cache
+
+        cfg = tf.Gemma2Config(**GEMMA2_9B)
+        tf.set_seed(42)
+        with torch.device("cuda"):
+            model = tf.Gemma2ForCausalLM._from_config(cfg, attn_implementation="b200", dtype=BF)
+        transformers_b200.accelerate(model)
+        model.eval()
+        P, Dn = 8192, 512
+        torch.manual_seed(0)
+        ids_host = torch.randint(1, cfg.vocab_size, (1, P), dtype=torch.int64).pin_memory()
+
+        def run(new_tokens):  # the user-facing call: ids from host memory, generated tokens back on the host
+            cache = make_cache(model.config)
+            with torch.no_grad():
+                out = model.generate(ids_host.cuda(non_blocking=True), max_new_tokens=new_tokens, min_new_tokens=new_tokens,
+                                     do_sample=False, pad_token_id=0, past_key_values=cache)
+            return out.cpu()
+
+        run(4)
+        sampler.start()
+        ms_prefill, _ = _event_ms(lambda: run(1), 2)
+        n0 = ops.launch_count()
+        ms_total, _ = _event_ms(lambda: run(Dn), 1)
+        launches = ops.launch_count() - n0
+        sampler.stop_flag = True
+        ms_decode = max(ms_total - ms_prefill, 1e-3) / (Dn - 1)
+        n_par = sum(p.numel() for p in model.parameters())
+        # bytes one decode step must read: every weight once (tied embedding counted once: the head reads it, the gather reads
+        # one row) + the KV cache (21 full layers over the whole context, 21 sliding layers over <= 4095 rows)
+        kv = 21 * 2 * 8 * 256 * 2 * (P + Dn / 2) + 21 * 2 * 8 * 256 * 2 * 4095
+        step_bytes = n_par * 2 + kv
+        gbs = step_bytes / (ms_decode * 1e-3) / 1e9
+        prefill_tf = (2 * (n_par - cfg.vocab_size * cfg.hidden_size) + 2 * cfg.vocab_size * cfg.hidden_size / P) * P / (ms_prefill * 1e-3) / 1e12
+        line = {**base, "steps": 1, "metric": "decode tokens/sec Gemma-2-9B generate() prefill 8192 + decode 512",
+                "value": 1e3 / ms_decode, "unit": "tokens/s", "ms_per_step": ms_decode,
+                "prefill": {"tokens_per_s": P / (ms_prefill * 1e-3), "ms": ms_prefill, "linear_tflops": prefill_tf},
+                "config": {"workload": "Gemma-2-9B generate(): prefill 8192 + decode 512 on 1xB200 (configs[4])",
+                           "model": "Gemma-2-9B (random init)", "global_batch": 1, "seq_len": P + Dn, "parallelism": "single",
+                           "cache": "transformers_b200.cache.make_cache: in-place append, in-place sliding window",
+                           "l2": "18.5 GB of weights per decode step >> 126 MB L2; no explicit flush needed"},
+                "e2e": {"value": Dn / (ms_total * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": P * 8, "d2h_bytes_per_step": (P + Dn) * 8,
+                        "ms_per_step": ms_total, "note": "whole generate() call (prefill + 512 decode steps) per 512 new tokens"},
+                "gpu_launches": launches,
+                "roofline": {"bound": "hbm", "kernel": "one decode step (weight-streaming GEMVs + split-context attention)",
+                             "achieved": gbs, "peak": peak_bw, "unit": "GB/s", "frac": gbs / peak_bw,
+                             "peak_source": "measured copy bandwidth (MEASURED_PEAKS.json)" if peaks else "fallback",
+                             "traffic": None, "bytes_per_step": step_bytes}}
+    else:  # llama3-8b-trainer-step
+        from transformers_b200.optim import B200AdamW
+
+        cfg = tf.LlamaConfig(**{**LLAMA3_8B, "num_hidden_layers": args.layers, "use_cache": False})
+        tf.set_seed(42)
+        with torch.device("cuda"):
+            model = tf.LlamaForCausalLM._from_config(cfg, attn_implementation="b200", dtype=BF)
+        transformers_b200.accelerate(model)
+        model.train()
+        opt = B200AdamW(model.parameters(), lr=1e-5, betas=(0.9, 0.95), weight_decay=0.1, max_grad_norm=1.0)
+        B, S = args.batch, args.seq
+        torch.manual_seed(0)
+        ids_host = torch.randint(0, cfg.vocab_size, (B, S), dtype=torch.int64).pin_memory()
+        ids_dev, stage = ids_host.cuda(), torch.empty(B, S, dtype=torch.int64, device="cuda")
+
+        def resident():  # what Trainer.training_step + the optimizer step do (trainer.py:1784-1788), clip fused into the update
+            loss = model(input_ids=ids_dev, labels=ids_dev).loss
+            loss.backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            return loss
+
+        def e2e():
+            stage.copy_(ids_host, non_blocking=True)
+            loss = model(input_ids=stage, labels=stage).loss
+            loss.backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            return loss.item()
+
+        for _ in range(warmup):
+            resident()
+        n0 = ops.launch_count()
+        sampler.start()
+        ms, loss = _event_ms(resident, steps)
+        launches = (ops.launch_count() - n0) // steps
+        ms_e2e, _ = _event_ms(e2e, steps)
+        sampler.stop_flag = True
+        tfs = FLOPS_PER_TOKEN_FWD_BWD * (args.layers / 32) * B * S / (ms * 1e-3) / 1e12
+        line = {**base, "metric": "tokens/sec Llama-3-8B Trainer-shaped step (fwd + bwd + clip + AdamW) seq4096",
+                "value": B * S / (ms * 1e-3), "unit": "tokens/s", "ms_per_step": ms, "loss": float(loss.detach()),
+                "config": {"workload": f"Llama-3-8B bf16 fwd+bwd+grad-clip+AdamW seq={S} batch={B} on 1xB200 (SURVEY 8f-2)"
+                           if args.layers == 32 else f"DEBUG {args.layers}-layer model", "model": "Llama-3-8B (random init)",
+                           "global_batch": B, "seq_len": S, "parallelism": "single",
+                           "optimizer": "transformers_b200.optim.B200AdamW(max_grad_norm=1.0): bf16 moments, clip fused into the update"},
+                "e2e": {"value": B * S / (ms_e2e * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": B * S * 8, "d2h_bytes_per_step": 4,
+                        "ms_per_step": ms_e2e},
+                "gpu_launches": launches,
+                "roofline": {"bound": "tensor", "kernel": "whole step (model FLOPs; the optimizer adds 14 B/parameter of HBM traffic)",
+                             "achieved": tfs, "peak": peak_tf, "unit": "TFLOP/s", "frac": tfs / peak_tf,
+                             "peak_source": "measured sustained (MEASURED_PEAKS.json)" if peaks else "fallback", "traffic": None}}
+    sampler.join(timeout=2)
+    line["clocks"] = sampler.summary()
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config != "llama3-8b-train":
+        run_secondary(args)
     else:
         run_b200(args)
 

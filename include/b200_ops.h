@@ -34,10 +34,6 @@ int b200_gemv_bf16(const void* x, const void* W, void* y, int M, int N, int K, i
 /* CTA-pair variant (tcgen05 cta_group::2, 256x256 tile per 2-CTA cluster); b200_gemm_bf16 dispatches to it for M > 128 */
 int b200_gemm_bf16_2sm(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
                        int b_mn, int accumulate, b200_stream_t stream);
-/* tuning knobs of the CTA-pair kernel for sweeps (process-wide; defaults are the measured optimum): M tiles per
- * rasterisation group (0 = unchanged) and, per layout (NT fwd / NN dgrad / TT wgrad), the smallest K from which the
- * lock-step variant runs (0 = never, < 0 = unchanged) */
-int b200_gemm_tuning(int group_m, int sync_min_k_nt, int sync_min_k_nn, int sync_min_k_tt);
 /* 1-CTA variant (128x256 tiles); b200_gemm_bf16 dispatches to it for M <= 128 */
 int b200_gemm_bf16_1sm(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
                        int b_mn, int accumulate, b200_stream_t stream);

@@ -112,10 +112,10 @@ def test_mixtral_moe_backward_matches_oracle():
     tw, ti = O.moe_router(x, w_gate, k)
     ti = torch.where(ti == 3, torch.full_like(ti, 2), ti)  # one expert receives no token
     dout = rnd(T, H)
-    ref_in = [t.float().requires_grad_(True) for t in (x, tw, gate_up, down)]
+    ref_in = [t.detach().clone().float().requires_grad_(True) for t in (x, tw, gate_up, down)]
     ref = O.moe_experts(ref_in[0], ti, ref_in[1], ref_in[2], ref_in[3])
     ref.backward(dout.float())
-    ours_in = [t.cuda().requires_grad_(True) for t in (x, tw.to(torch.bfloat16), gate_up, down)]
+    ours_in = [t.detach().to(torch.bfloat16).cuda().requires_grad_(True) for t in (x, tw, gate_up, down)]
     out = Fn.MoEExpertsFn.apply(ours_in[0], ti.cuda(), ours_in[1], ours_in[2], ours_in[3], False)
     out.backward(dout.cuda())
     rel = lambda a, b: ((a.float().cpu() - b).abs().max() / (b.abs().max() + 1e-8)).item()

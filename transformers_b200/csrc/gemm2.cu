@@ -29,10 +29,6 @@ struct Gemm2Params {
   int accumulate;
   int group_m;
   uint32_t a_lbo, a_sbo, b_lbo, b_sbo;
-  // SYNC variant only: soft lock-step of the clusters at tile boundaries (see soft_grid_sync)
-  unsigned long long* sync_ctr;
-  unsigned long long sync_base;
-  int sync_rounds;
   // SCATTER variant only: row block r (rows_per_owner rows) of the output goes to scatter_maps[r] (tensor maps in global
   // memory, one per destination buffer -- peer-mapped memory of rank r); m_rot rotates the tile order so that the blocks
   // of the other ranks are produced (and travel over NVLink) first, the own block last
@@ -41,26 +37,11 @@ struct Gemm2Params {
   int m_rot;
 };
 
-constexpr int G2_MODE_PLAIN = 0, G2_MODE_SYNC = 1, G2_MODE_SCATTER = 2;
+constexpr int G2_MODE_PLAIN = 0, G2_MODE_SCATTER = 2;
 
-// Co-running tiles share A row panels / B column panels through L2 only while they walk K together.  Nothing keeps the
-// 74 persistent clusters in step: after a few tiles their start times have drifted by more than L2 can bridge and the
-// same k-blocks are fetched from DRAM again (ncu: 4.9-10.6 GB per launch where 1.3 GB is algorithmic, profiles/README.md).
-// The SYNC variant re-aligns them: at the start of every tile round each cluster's producer bumps a global counter and
-// waits (bounded: 20 us, then goes on -- the wait is an optimisation, never needed for correctness, so a cluster that is
-// not resident yet, e.g. behind a concurrent NCCL kernel, cannot deadlock the others) until all clusters of the round have
-// arrived.  The six buffered stages keep the tensor core busy meanwhile.  The counter is monotonic across launches
-// (sync_base = its value before this launch; launches are stream-ordered).
-__device__ unsigned long long g_gemm2_sync_ctr = 0ull;
-
-__device__ __forceinline__ void soft_grid_sync(unsigned long long* ctr, unsigned long long target) {
-  atomicAdd(ctr, 1ull);
-  const uint64_t t0 = global_timer_ns();
-  while (*reinterpret_cast<volatile unsigned long long*>(ctr) < target) {
-    if (global_timer_ns() - t0 > 20000ull) break;
-  }
-}
-
+// (A soft lock-step of the persistent clusters at tile boundaries -- to keep co-running tiles walking K together and cut
+// the DRAM re-reads -- was measured in round 2: no step-time gain on the Llama-3-8B shapes, so it is gone;
+// profiles/r02_call3a_gemm_tuning.md.)
 template <int A_MN, int B_MN, int MODE>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -104,7 +85,6 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  constexpr bool SYNC = MODE == G2_MODE_SYNC;
   constexpr bool SCATTER = MODE == G2_MODE_SCATTER;
 
   auto tile_coords = [&](int tile, int& tm, int& tn) {
@@ -125,12 +105,7 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (elect_one()) {  // elect.sync: the compiler keeps UTCHMMA / UTMALDG operands in uniform registers (no per-op ELECT loop)
       int stage = 0;
       uint32_t phase = 0;
-      [[maybe_unused]] int round = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        if constexpr (SYNC) {
-          ++round;
-          if (rank == 0) soft_grid_sync(p.sync_ctr, p.sync_base + static_cast<unsigned long long>(round) * num_clusters);
-        }
         int tm, tn;
         tile_coords(tile, tm, tn);
         const int m0 = tm * G2_BM + rank * 128;
@@ -157,11 +132,6 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             stage = 0;
             phase ^= 1;
           }
-        }
-      }
-      if constexpr (SYNC) {  // a cluster without a tile in the last round still arrives, so nobody waits for it
-        if (rank == 0) {
-          for (; round < p.sync_rounds; ++round) atomicAdd(p.sync_ctr, 1ull);
         }
       }
     }
@@ -314,21 +284,9 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   }
 }
 
-// Tuning knobs of the CTA-pair GEMM, set through b200_gemm_tuning() (an explicit host call for sweeps; NOT read from the
-// environment): rasterisation group size and, per operand layout, the smallest K from which the lock-step variant runs
-// (0 = never).  Defaults = what measured best on the Llama-3-8B step (profiles/README.md, round 2).
-static int g_group_m = 8;
-static int g_sync_min_k[2][2] = {{0, 0}, {0, 0}};  // [a_mn][b_mn]
-
-static bool gemm2_sync_wanted(int a_mn, int b_mn, int K) {
-  const int mk = g_sync_min_k[a_mn ? 1 : 0][b_mn ? 1 : 0];
-  return mk > 0 && K >= mk;
-}
-
 template <int A_MN, int B_MN, int MODE>
 static int launch_gemm2_v(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, Gemm2Params p,
                           cudaStream_t stream) {
-  constexpr bool SYNC = MODE == G2_MODE_SYNC;
   auto kern = gemm_bf16_tcgen05_2sm<A_MN, B_MN, MODE>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -343,15 +301,6 @@ static int launch_gemm2_v(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   }
   int clusters = sms / 2;
   if (num_tiles < clusters) clusters = num_tiles;
-  if (SYNC) {
-    static unsigned long long* ctr = nullptr;
-    static unsigned long long host_base = 0ull;
-    if (!ctr) B200_CHECK_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&ctr), g_gemm2_sync_ctr));
-    p.sync_ctr = ctr;
-    p.sync_base = host_base;
-    p.sync_rounds = (num_tiles + clusters - 1) / clusters;
-    host_base += static_cast<unsigned long long>(p.sync_rounds) * clusters;
-  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * 2);
   cfg.blockDim = dim3(G2_THREADS);
@@ -372,8 +321,7 @@ template <int A_MN, int B_MN>
 static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const Gemm2Params& p,
                         cudaStream_t stream) {
   if (p.scatter_maps) return launch_gemm2_v<A_MN, B_MN, G2_MODE_SCATTER>(tmA, tmB, tmC, p, stream);
-  return gemm2_sync_wanted(A_MN, B_MN, p.K) ? launch_gemm2_v<A_MN, B_MN, G2_MODE_SYNC>(tmA, tmB, tmC, p, stream)
-                                            : launch_gemm2_v<A_MN, B_MN, G2_MODE_PLAIN>(tmA, tmB, tmC, p, stream);
+  return launch_gemm2_v<A_MN, B_MN, G2_MODE_PLAIN>(tmA, tmB, tmC, p, stream);
 }
 
 }  // namespace b200
@@ -408,13 +356,10 @@ static int gemm2_run(const void* A, const void* B, void* C, int M, int N, int K,
   p.K = K;
   p.ldc = ldc;
   p.accumulate = accumulate;
-  p.sync_ctr = nullptr;
-  p.sync_base = 0ull;
-  p.sync_rounds = 0;
   p.scatter_maps = scatter_maps;
   p.rows_per_owner = rows_per_owner;
   p.m_rot = m_rot;
-  p.group_m = b200::g_group_m;  // M tiles per rasterisation group (wave footprint ~ group_m x 74/group_m tiles of 256x256)
+  p.group_m = 8;  // M tiles per rasterisation group (wave footprint ~ 8 x 9.25 tiles of 256x256); 4 and 16 measured no better
   const uint32_t k_lbo = 16, k_sbo = 1024, mn_lbo = 64 * G2_BK * 2, mn_sbo = 1024;
   p.a_lbo = a_mn ? mn_lbo : k_lbo;
   p.a_sbo = a_mn ? mn_sbo : k_sbo;
@@ -424,18 +369,6 @@ static int gemm2_run(const void* A, const void* B, void* C, int M, int N, int K,
   if (!a_mn && b_mn) return launch_gemm2<0, 1>(tmA, tmB, tmC, p, stream);
   if (a_mn && b_mn) return launch_gemm2<1, 1>(tmA, tmB, tmC, p, stream);
   return launch_gemm2<1, 0>(tmA, tmB, tmC, p, stream);
-}
-
-// group_m: M tiles per rasterisation group (1..64; 0 = leave unchanged).  sync_min_k_*: smallest K from which the
-// lock-step variant is used for that layout (NT = forward, NN = dgrad, TT = wgrad); 0 = never, < 0 = leave unchanged.
-// Process-wide; intended for sweeps (tests/cuda) -- the defaults are the measured optimum.
-extern "C" int b200_gemm_tuning(int group_m, int sync_min_k_nt, int sync_min_k_nn, int sync_min_k_tt) {
-  B200_REQUIRE(group_m >= 0 && group_m <= 64, "gemm_tuning: group_m %d outside 0..64", group_m);
-  if (group_m > 0) b200::g_group_m = group_m;
-  if (sync_min_k_nt >= 0) b200::g_sync_min_k[0][0] = sync_min_k_nt;
-  if (sync_min_k_nn >= 0) b200::g_sync_min_k[0][1] = sync_min_k_nn;
-  if (sync_min_k_tt >= 0) b200::g_sync_min_k[1][1] = sync_min_k_tt;
-  return B200_OK;
 }
 
 // Same contract as b200_gemm_bf16 (gemm.cu); requires M > 128 to be worthwhile.  Called by the dispatcher there.

@@ -81,11 +81,6 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     return out
 
 
-def gemm_tuning(group_m: int = 0, sync_min_k_nt: int = -1, sync_min_k_nn: int = -1, sync_min_k_tt: int = -1) -> None:
-    """Sweep knobs of the CTA-pair GEMM (include/b200_ops.h: b200_gemm_tuning); process-wide."""
-    _check(_lib.load().b200_gemm_tuning(int(group_m), int(sync_min_k_nt), int(sync_min_k_nn), int(sync_min_k_tt)), "b200_gemm_tuning")
-
-
 # ------------------------------------------------------------------------------------------------------ embedding
 def embedding_fwd(ids: torch.Tensor, weight: torch.Tensor, scale: float | None = None) -> torch.Tensor:
     lib = _lib_ready()
