@@ -207,7 +207,7 @@ def ce_fwd(logits, labels, shift=True, ignore_index=-100, num_items=None):
     return (nll.sum() / denom[0]).to(torch.float32), lse, denom
 
 
-def ce_bwd(logits, labels, lse, dloss, denom, shift=True, ignore_index=-100):
+def ce_bwd(logits, labels, lse, dloss, denom, shift=True, ignore_index=-100, out=None):
     B, S, V = logits.shape
     tgt = _ce_targets(labels, B, S, shift, ignore_index)
     lg = logits.reshape(B * S, V).float()
@@ -216,6 +216,9 @@ def ce_bwd(logits, labels, lse, dloss, denom, shift=True, ignore_index=-100):
     p[torch.arange(B * S)[valid], tgt[valid]] -= 1.0
     p = p * valid[:, None] * (dloss.reshape(()).float() / denom[0])
     _log("ce_bwd", logits)
+    if out is not None:
+        out.copy_(p.to(logits.dtype))
+        return out.view(B, S, V)
     return p.to(logits.dtype).view(B, S, V)
 
 

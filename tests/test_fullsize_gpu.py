@@ -107,7 +107,7 @@ def test_llama3_8b_full_width_layer_fwd_bwd_vs_fp32_oracle():
     tf.set_seed(42)
     with torch.device("cuda"):
         model = tf.LlamaForCausalLM._from_config(cfg, attn_implementation="b200", dtype=BF)
-    transformers_b200.accelerate(model)
+    transformers_b200.accelerate(model, fused_head_loss=False)
     model.train()
     with torch.no_grad():
         for n, p in model.named_parameters():
@@ -140,3 +140,18 @@ def test_llama3_8b_full_width_layer_fwd_bwd_vs_fp32_oracle():
         assert p.grad is not None, n
         rel = _rel(p.grad, ref)
         assert rel < 3e-2, f"grad {n}: rel err {rel}"
+    # the same step through the chunked fused lm_head + loss (what accelerate() installs by default for training forwards):
+    # no [T, V] logits, same loss, same gradients
+    from transformers_b200.integration import _install_fused_head_loss
+
+    loss_unfused = out.loss.item()
+    del out, logits_ref, lo32
+    model.zero_grad(set_to_none=True)
+    _install_fused_head_loss(model)
+    out2 = model(input_ids=ids, labels=ids)
+    assert out2.logits.shape[-1] == 0
+    out2.loss.backward()
+    assert abs(out2.loss.item() - loss_unfused) < 2e-3, (out2.loss.item(), loss_unfused)
+    for n, p in model.named_parameters():
+        rel = _rel(p.grad, p32[n].grad)
+        assert rel < 3e-2, f"fused head+loss, grad {n}: rel err {rel}"

@@ -32,8 +32,9 @@ def _llama_cfg(**kw):
     return transformers.LlamaConfig(**base)
 
 
-def _pair(cls, cfg):
-    """(stock eager model, accelerated copy on the faked kernel path) with identical weights."""
+def _pair(cls, cfg, fused_head_loss=False):
+    """(stock eager model, accelerated copy on the faked kernel path) with identical weights.  ``fused_head_loss`` is off
+    unless a test is about it: most tests compare the logits of training-mode forwards, which that path does not produce."""
     from transformers.monkey_patching import clear_patch_mapping
 
     import transformers_b200.integration as integ
@@ -46,7 +47,7 @@ def _pair(cls, cfg):
         integ._enabled = False
         transformers_b200.enable()
     ours = copy.deepcopy(ref)
-    transformers_b200.accelerate(ours)
+    transformers_b200.accelerate(ours, fused_head_loss=fused_head_loss)
     return ref, ours
 
 
@@ -298,7 +299,7 @@ def test_fused_residual_decoder_layer_matches_the_stock_layer():
                                                  num_attention_heads=4, num_key_value_heads=2, head_dim=16, sliding_window=8,
                                                  max_position_embeddings=128))):
         ref, ours = _pair(cls, cfg)
-        transformers_b200.accelerate(ours, fuse_residual=True)
+        transformers_b200.accelerate(ours, fuse_residual=True, fused_head_loss=False)
         assert type(ours.model.layers[0]).__name__.startswith("B200")
         torch.manual_seed(14)
         _compare(ref, ours, torch.randint(0, 160, (2, 20)))
@@ -412,3 +413,45 @@ def test_masks_the_kernels_cannot_express_raise():
                and_masks(chunked_overlay(4, torch.zeros(1, dtype=torch.int64)), causal_mask_function)):
         with pytest.raises(transformers_b200.B200Error):
             b200_attention_mask(1, 6, 6, mask_function=fn)
+
+
+# ------------------------------------------------------------------------------------- chunked fused lm_head + loss
+@pytest.mark.parametrize("variant", ["mean", "num_items", "padded_labels"])
+def test_fused_head_loss_matches_stock_head_and_loss(variant, monkeypatch):
+    """Training forward with labels: lm_head + ForCausalLMLoss run chunk by chunk without the [T, V] logits
+    (functional.FusedHeadLossFn: gradients produced inside the forward, wgrad accumulated across chunks).  Loss and every
+    gradient must equal the stock model's; ``out.logits`` is the documented empty placeholder; eval forwards, forwards
+    without labels and ``fused_head_loss=False`` still return logits."""
+    from transformers_b200 import functional as Fn
+
+    monkeypatch.setattr(Fn.FusedHeadLossFn, "CHUNK_ROWS", 16)  # T = 48 -> three chunks
+    ref, ours = _pair(transformers.LlamaForCausalLM, _llama_cfg(), fused_head_loss=True)
+    ref.train()
+    ours.train()
+    torch.manual_seed(5)
+    ids = torch.randint(0, 160, (2, 24))
+    labels = ids.clone()
+    kw = {}
+    if variant == "padded_labels":
+        labels[0, 5:11] = -100
+        labels[1, -4:] = -100
+    if variant == "num_items":
+        kw["num_items_in_batch"] = torch.tensor(37)
+    a = ref(input_ids=ids, labels=labels, use_cache=False, **kw)
+    a.loss.backward()
+    _fake_ops.CALLS.clear()
+    b = ours(input_ids=ids, labels=labels, use_cache=False, **kw)
+    assert b.logits.shape == (2, 24, 0)
+    (b.loss * 0.5).backward()  # a non-unit upstream gradient (Trainer divides by the accumulation steps)
+    torch.testing.assert_close(b.loss, a.loss, atol=1e-5, rtol=1e-5)
+    ga = dict(ref.named_parameters())
+    for n, p in ours.named_parameters():
+        torch.testing.assert_close(p.grad, 0.5 * ga[n].grad, atol=2e-5, rtol=1e-3, msg=lambda m, n=n: f"{n}: {m}")
+    names = [c[0] for c in _fake_ops.CALLS]
+    assert names.count("ce_fwd") == 3 and names.count("ce_bwd") == 3
+    with torch.no_grad():
+        assert ours(input_ids=ids, labels=labels, use_cache=False).logits.shape == (2, 24, 160)  # no grad: logits as usual
+    assert ours(input_ids=ids, use_cache=False).logits.shape == (2, 24, 160)
+    ours.eval()
+    torch.testing.assert_close(ours(input_ids=ids, labels=labels, use_cache=False).logits,
+                               ref.eval()(input_ids=ids, use_cache=False).logits, atol=2e-5, rtol=1e-4)

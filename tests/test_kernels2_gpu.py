@@ -225,7 +225,7 @@ def test_gemma_v1_forward_backward_matches_oracle():
     with torch.no_grad():
         lobf, _, _ = O.model_forward(ids, {k: v.clone() for k, v in sd.items()}, ocfg, labels=ids)
     model = model.cuda().train()
-    transformers_b200.accelerate(model)
+    transformers_b200.accelerate(model, fused_head_loss=False)
     assert type(model.model.layers[0].mlp).__name__ == "B200GemmaMLP"
     out = model(input_ids=ids.cuda(), labels=ids.cuda())
     out.loss.backward()

@@ -66,7 +66,7 @@ def test_forward_backward_matches_oracle(kind, padded):
         lobf, lossbf, _ = O.model_forward(ids, pbf, ocfg, labels=labels, padding_mask=am)
 
     model = model.cuda().train()
-    transformers_b200.accelerate(model)
+    transformers_b200.accelerate(model, fused_head_loss=False)  # this test compares the logits of a training-mode forward
     kw = {"attention_mask": am.cuda()} if padded else {}
     out = model(input_ids=ids.cuda(), labels=labels.cuda(), **kw)
     out.loss.backward()
@@ -246,3 +246,44 @@ def test_packed_batch_equals_separate_sequences():
         assert rel < 3e-2, f"{n}: {rel}"
     un = model(input_ids=ids, use_cache=False).logits  # and ignoring the boundaries gives a different answer
     assert (un.float() - out.logits.float()).abs().max() > 5e-2
+
+
+@pytest.mark.parametrize("masked_labels", [False, True])
+def test_fused_head_loss_training_step_matches_oracle(masked_labels):
+    """accelerate()'s default for training forwards with labels: lm_head + loss chunk by chunk, no [T, V] logits
+    (functional.FusedHeadLossFn; wgrad accumulated across chunks through the GEMM's TMA reduce-add epilogue).  Loss and all
+    gradients vs the fp32 oracle; three row chunks including a ragged last one."""
+    import transformers_b200
+    from transformers_b200 import functional as Fn
+
+    tf, cfg, model = _build("llama")
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    ocfg = O.config_from_hf(cfg)
+    torch.manual_seed(0)
+    B, S = 2, 200
+    ids = torch.randint(1, cfg.vocab_size, (B, S))
+    labels = ids.clone()
+    if masked_labels:
+        labels[0, 17:60] = -100
+        labels[1, -30:] = -100
+    p32 = {k: v.float().requires_grad_(True) for k, v in sd.items()}
+    _, loss32, _ = O.model_forward(ids, p32, ocfg, labels=labels)
+    loss32.backward()
+    model = model.cuda().train()
+    transformers_b200.accelerate(model)
+    old = Fn.FusedHeadLossFn.CHUNK_ROWS
+    Fn.FusedHeadLossFn.CHUNK_ROWS = 160  # T = 400 -> chunks of 160, 160, 80
+    try:
+        out = model(input_ids=ids.cuda(), labels=labels.cuda())
+        assert out.logits.shape == (B, S, 0)
+        out.loss.backward()
+    finally:
+        Fn.FusedHeadLossFn.CHUNK_ROWS = old
+    assert abs(out.loss.item() - loss32.item()) < 2e-2
+    for n, p in model.named_parameters():
+        ref = p32[n].grad
+        rel = ((p.grad.float().cpu() - ref).abs().max() / (ref.abs().max() + 1e-8)).item()
+        assert rel < 5e-2, f"grad {n}: rel err {rel:.4f}"
+    model.eval()
+    with torch.no_grad():
+        assert model(input_ids=ids.cuda(), labels=labels.cuda()).logits.shape == (B, S, cfg.vocab_size)

@@ -177,12 +177,12 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const int buf = it & 1;
       mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
       tc_fence_after();
-      const int row = tm * G2_BM + rank * 128 + q * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * G2_BN;
       const int ncols = min(G2_BN, p.N - tn * G2_BN);
-      if (!p.accumulate) {
+      {
         // TMEM -> registers -> bf16 -> 128B-swizzled smem tile (32 rows x 64 cols) -> one TMA store per chunk: full-line
-        // writes, no per-thread global stores, M / N tails clipped by the tensor map
+        // writes, no per-thread global stores, M / N tails clipped by the tensor map.  accumulate: the same tile goes out
+        // as a TMA reduce-add (C += tile, bf16 adds performed at L2) -- no read-modify-write through the SM
         uint8_t* stage = epi_smem + (warp - 2) * 8192;
         const int row0 = tm * G2_BM + rank * 128 + q * 32;
 #pragma unroll 1
@@ -215,6 +215,8 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             if constexpr (SCATTER) {  // the 32-row strip lives in exactly one owner's buffer (rows_per_owner % 256 == 0)
               const int owner = row0 / p.rows_per_owner;
               tma_store_2d(p.scatter_maps + owner, sbuf, tn * G2_BN + c * 64, row0 - owner * p.rows_per_owner);
+            } else if (p.accumulate) {
+              tma_reduce_add_2d(&tmC, sbuf, tn * G2_BN + c * 64, row0);
             } else {
               tma_store_2d(&tmC, sbuf, tn * G2_BN + c * 64, row0);
             }
@@ -225,53 +227,7 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[buf]), 0));  // accumulator drained: tell the leader
         if (lane == 0) tma_store_wait_read<0>();  // staging buffers free before the next tile
         __syncwarp();
-        continue;
       }
-      __nv_bfloat16* crow = p.C + static_cast<size_t>(row) * p.ldc + tn * G2_BN;
-#pragma unroll 1
-      for (int c = 0; c < G2_BN / 32; ++c) {
-        if (c * 32 >= ncols) break;
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(taddr + c * 32, r);
-        tmem_ld_wait();
-        if (row < p.M) {
-#pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            const int col = c * 32 + v * 8;
-            if (col + 8 <= ncols) {
-              uint4* dst = reinterpret_cast<uint4*>(crow + col);
-              float f[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[v * 8 + e]);
-              {
-                uint4 old = *dst;
-                const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&old);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float2 of = __bfloat1622float2(o2[e]);
-                  f[2 * e] += of.x;
-                  f[2 * e + 1] += of.y;
-                }
-              }
-              uint4 o;
-              o.x = pack_bf16(f[0], f[1]);
-              o.y = pack_bf16(f[2], f[3]);
-              o.z = pack_bf16(f[4], f[5]);
-              o.w = pack_bf16(f[6], f[7]);
-              *dst = o;
-            } else {
-              for (int e = 0; e < 8; ++e) {
-                if (col + e < ncols) {
-                  float f = __uint_as_float(r[v * 8 + e]) + __bfloat162float(crow[col + e]);
-                  crow[col + e] = __float2bfloat16_rn(f);
-                }
-              }
-            }
-          }
-        }
-      }
-      tc_fence_before();
-      mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[buf]), 0));  // accumulator drained: tell the leader
     }
   }
 

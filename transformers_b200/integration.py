@@ -207,6 +207,10 @@ def b200_causal_lm_loss(logits, labels, vocab_size=None, num_items_in_batch=None
         raise B200Error("b200 loss: expects CUDA bf16 logits")
     if torch.is_tensor(num_items_in_batch):
         num_items_in_batch = float(num_items_in_batch)
+    lazy = getattr(logits, "_b200_lazy_head", None)
+    if lazy is not None:  # lm_head skipped the logits (accelerate(fused_head_loss=True), training forward with labels)
+        h, w_fused, w_param = lazy
+        return Fn.FusedHeadLossFn.apply(h, w_fused, labels, ignore_index, num_items_in_batch, shift, w_param)
     shard_group = getattr(logits, "_b200_vocab_shard", None)
     if shard_group is not None:  # lm_head left its output vocabulary-sharded (parallel.tensor_parallelize(vocab_parallel_loss=True))
         return Fn.VocabParallelLossFn.apply(logits, labels, ignore_index, num_items_in_batch, shift, shard_group)
@@ -216,12 +220,38 @@ def b200_causal_lm_loss(logits, labels, vocab_size=None, num_items_in_batch=None
     return Fn.CausalLMLossFn.apply(logits, labels, ignore_index, num_items_in_batch, shift)
 
 
+def _install_fused_head_loss(model: nn.Module) -> None:
+    """Training forwards that carry ``labels`` (and use our loss) do not materialise the logits: lm_head hands hidden states
+    and weight to the loss, which walks the tokens in chunks (functional.FusedHeadLossFn).  ``out.logits`` of such a forward
+    is an empty [B, S, 0] placeholder -- like the fused linear-cross-entropy kernels the reference points at
+    (integrations/hub_kernels.py:509-515); eval-mode forwards and forwards without labels return logits as usual."""
+    head = model.lm_head
+    if model.__dict__.get("_b200_fused_head_hooks"):
+        return
+
+    def before(module, args, kwargs):
+        ours = getattr(module, "loss_function", None) is b200_causal_lm_loss
+        keep = kwargs.get("logits_to_keep", 0)
+        head.__dict__["_b200_lazy_logits"] = bool(ours and module.training and kwargs.get("labels") is not None
+                                                   and isinstance(keep, int) and keep == 0
+                                                   and not head.__dict__.get("_b200_keep_vocab_shard", False))
+
+    def after(module, args, kwargs, output):
+        head.__dict__["_b200_lazy_logits"] = False
+
+    model.register_forward_pre_hook(before, with_kwargs=True)
+    model.register_forward_hook(after, with_kwargs=True, always_call=True)
+    model.__dict__["_b200_fused_head_hooks"] = True
+
+
 def accelerate(model: nn.Module, attn: bool = True, head_and_loss: bool = True, pack_weights: bool = False,
-               fuse_residual: bool = True) -> nn.Module:
+               fuse_residual: bool = True, fused_head_loss: bool = True) -> nn.Module:
     """Convert an already constructed reference model in place (class swap, parameters untouched).
     ``pack_weights``: additionally make q/k/v and gate/up weights row views of one buffer (modules.pack_weights).
     ``fuse_residual`` (default): Llama / Mistral decoder layers run their residual adds on our kernels, the first fused
-    with the post-attention RMSNorm (modules.B200DecoderLayerMixin); False keeps the reference's ``torch.add``."""
+    with the post-attention RMSNorm (modules.B200DecoderLayerMixin); False keeps the reference's ``torch.add``.
+    ``fused_head_loss`` (default): training forwards with labels run lm_head + loss chunk by chunk without materialising the
+    [T, V] logits (``_install_fused_head_loss``); False always returns logits."""
     enable()
     cmap = _class_map()
     by_base = {cls.__mro__[2]: cls for cls in cmap.values()}  # (B200X, mixin, base, ...)
@@ -235,6 +265,8 @@ def accelerate(model: nn.Module, attn: bool = True, head_and_loss: bool = True, 
         model.lm_head.__class__ = M.make_class(nn.Linear, M.B200LinearMixin)
         if getattr(model.config, "final_logit_softcapping", None) is None:
             model.loss_function = b200_causal_lm_loss
+            if fused_head_loss:
+                _install_fused_head_loss(model)
     if attn and hasattr(model, "set_attn_implementation"):
         model.set_attn_implementation(ATTN_NAME)
     if attn and any(hasattr(m, "gate_up_proj") and hasattr(m, "num_experts") for m in model.modules()):

@@ -355,6 +355,13 @@ class B200LinearMixin:
     def forward(self, x):
         w = _local(self.weight)
         gather = self.__dict__.get("_b200_tp_gather", False)
+        if (self.__dict__.get("_b200_lazy_logits", False) and not gather and _on_b200(w) and self.bias is None
+                and x.dtype in KERNEL_DTYPES and torch.is_grad_enabled()):
+            # training forward with labels and our loss (integration._install_fused_head_loss): skip the [T, V] logits; the
+            # loss function finds hidden states and weight on the placeholder and runs functional.FusedHeadLossFn
+            y = x.new_empty(*x.shape[:-1], 0)
+            y._b200_lazy_head = (x, fused_weight(self, "w", [w]), self.weight)
+            return y
         if not _on_b200(w) or self.bias is not None:
             y = super().forward(_tp_copy(self, x) if gather else x)
         else:

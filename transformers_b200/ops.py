@@ -241,7 +241,7 @@ def _lse_stride(sq: int) -> int:
 
 
 def attn_fwd(q, k, v, *, scale: float, causal: bool, window: int = 0, softcap: float = 0.0, kv_start=None, kv_end=None,
-             out: torch.Tensor | None = None, decode_kernel: bool | None = None):
+             out: torch.Tensor | None = None, decode_kernel: bool | None = None, one_tile_kernel: bool = False):
     """q [B,Sq,Hq,D], k/v [B,Skv,Hkv,D] strided views -> (out [B,Sq,Hq,D], lse [B,Hq,lse_stride] fp32).
     q_len == 1 goes to the split-context decode kernels (``decode_kernel=False`` forces the tensor-core kernel: tests)."""
     lib = _lib_ready()
@@ -264,7 +264,8 @@ def attn_fwd(q, k, v, *, scale: float, causal: bool, window: int = 0, softcap: f
                                    kv_start.data_ptr() if kv_start is not None else None,
                                    kv_end.data_ptr() if kv_end is not None else None, _stream()), "b200_attn_decode")
         return out, lse
-    check(lib.b200_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(), ls, B, Sq, Skv, Hq, Hkv, D,
+    entry = lib.b200_attn_fwd_1tile if one_tile_kernel else lib.b200_attn_fwd
+    check(entry(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(), ls, B, Sq, Skv, Hq, Hkv, D,
                             *_bsh_strides(q), *_bsh_strides(k), *_bsh_strides(v), *_bsh_strides(out), float(scale),
                             float(softcap or 0.0), int(causal), int(window or 0),
                             kv_start.data_ptr() if kv_start is not None else None,
@@ -409,14 +410,18 @@ def ce_fwd(logits: torch.Tensor, labels: torch.Tensor, shift: bool = True, ignor
 
 
 def ce_bwd(logits: torch.Tensor, labels: torch.Tensor, lse: torch.Tensor, dloss: torch.Tensor, denom: torch.Tensor,
-           shift: bool = True, ignore_index: int = -100) -> torch.Tensor:
+           shift: bool = True, ignore_index: int = -100, out: torch.Tensor | None = None) -> torch.Tensor:
     lib = _lib_ready()
     B, S, V = logits.shape
     lg = logits.reshape(B * S, V)
     if not lg.is_contiguous():
         lg = lg.contiguous()
     labels = labels.contiguous().to(torch.int64)
-    dl = torch.empty(B * S, V, device=logits.device, dtype=BF16)
+    if out is not None:
+        _chk_bf16(out)
+        if out.shape != (B * S, V) or not out.is_contiguous():
+            raise B200Error("ce_bwd: `out` must be a contiguous [B*S, V] bf16 tensor")
+    dl = out if out is not None else torch.empty(B * S, V, device=logits.device, dtype=BF16)
     dloss = dloss.reshape(1).to(torch.float32).contiguous()
     check(lib.b200_ce_bwd(lg.data_ptr(), labels.data_ptr(), lse.data_ptr(), dloss.data_ptr(), denom.data_ptr(), dl.data_ptr(), B, S,
                           V, lg.stride(0), V, int(shift), int(ignore_index), _stream()), "b200_ce_bwd")
