@@ -78,6 +78,9 @@ def parse():
                          "0 = the reference's torch.add")
     ap.add_argument("--pack-weights", type=int, default=int(os.environ.get("B200_PACK_WEIGHTS", "0")),
                     help="make q/k/v and gate/up weights row views of one buffer (no second fused copy in HBM)")
+    ap.add_argument("--fused-head-loss", type=int, default=1, help="0 = materialise the logits (GEMM + CE kernels) instead of the chunked fused lm_head + loss")
+    ap.add_argument("--fuse-glu", type=int, default=1, help="0 = gate|up GEMM + separate GLU kernel instead of the GLU-epilogue GEMM")
+    ap.add_argument("--attn-one-tile", type=int, default=0, help="1 = attention forward on the one-tile kernel (A/B against the two-tile ping-pong kernel)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--config", default="llama3-8b-train",
                     choices=["llama3-8b-train", "llama3-8b-trainer-step", "mixtral-8x7b-forward", "gemma2-9b-generate"],
@@ -367,6 +370,8 @@ class TimedLib:
             if name == "b200_gemm_bf16_scatter":  # (A, B, dest, world, rank, M, N, K, lda, ldb, ldc, a_mn, b_mn, stream)
                 tag = f"gemm+scatter[{'T' if a[11] else 'N'}{'T' if a[12] else 'N'}]"
                 self.records.append((tag, e0, e1, 2.0 * a[5] * a[6] * a[7]))
+            elif name == "b200_gemm_glu_bf16":  # (A, W, gu, h, M, I, K, ...): a [M, 2I, K] GEMM with the activation in its epilogue
+                self.records.append(("gemm+glu[NT]", e0, e1, 2.0 * a[4] * 2 * a[5] * a[6]))
             elif name.startswith("b200_gemm_bf16"):
                 tag = f"gemm[{'T' if a[9] else 'N'}{'T' if a[10] else 'N'}]"
                 self.records.append((tag, e0, e1, 2.0 * a[3] * a[4] * a[5]))
@@ -414,7 +419,9 @@ def run_b200(args):
     transformers.set_seed(42)
     with torch.device("cuda"):
         model = transformers.LlamaForCausalLM._from_config(cfg, attn_implementation="b200", dtype=torch.bfloat16)
-    transformers_b200.accelerate(model, fuse_residual=bool(args.fuse_residual))
+    transformers_b200.accelerate(model, fuse_residual=bool(args.fuse_residual), fused_head_loss=bool(args.fused_head_loss),
+                                 fuse_glu=bool(args.fuse_glu))
+    ops.ATTN_ONE_TILE = bool(args.attn_one_tile)
     model.train()
     if parallelism == "tp":
         from transformers_b200.parallel import tensor_parallelize
@@ -522,7 +529,10 @@ def run_b200(args):
                                        + ("+vocab-parallel-loss" if parallelism == "tp" and args.vocab_parallel_loss else "")
                                        + (f"+{args.tp_transport}" if parallelism == "tp" and args.tp_transport != "nccl" else "")) if world > 1 else "single",
                        "l2": "working set (16 GB weights + activations) >> 126 MB L2; no explicit flush needed",
-                       "lm_head_and_loss": "included (b200 GEMM + fused CE kernels)"},
+                       "lm_head_and_loss": "included (chunked fused lm_head + loss: GEMM / CE kernels per 2048-row chunk, no [T, V] logits)"
+                       if args.fused_head_loss and parallelism != "tp" else "included (b200 GEMM + fused CE kernels)",
+                       "options": {"fuse_residual": args.fuse_residual, "fused_head_loss": args.fused_head_loss, "fuse_glu": args.fuse_glu,
+                                   "attn_one_tile": args.attn_one_tile}},
             "loss": float(loss.detach()), "model_tflops_per_gpu": per_gpu_tf,
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": ids_host.numel() * 8 * replicas,
                     "d2h_bytes_per_step": 4 * replicas, "ms_per_step": ms_e2e / args.steps},
@@ -608,7 +618,7 @@ def run_secondary(args):
         cfg = tf.MixtralConfig(**MIXTRAL_8X7B)
         tf.set_seed(42)
         with torch.device("cuda"):
-            model = tf.MixtralForCausalLM._from_config(cfg, attn_implementation="b200", dtype=BF)
+            model = tf.MixtralForCausalLM._from_config(cfg, attn_implementation="b200", experts_implementation="eager", dtype=BF)
         transformers_b200.accelerate(model)
         model.eval()
         S = 2048

@@ -34,6 +34,12 @@ int b200_gemv_bf16(const void* x, const void* W, void* y, int M, int N, int K, i
 /* CTA-pair variant (tcgen05 cta_group::2, 256x256 tile per 2-CTA cluster); b200_gemm_bf16 dispatches to it for M > 128 */
 int b200_gemm_bf16_2sm(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
                        int b_mn, int accumulate, b200_stream_t stream);
+/* gate|up projection + gated activation in ONE kernel (LlamaMLP.forward models/llama/modeling_llama.py:174-176): W is the
+ * [2I, K] block-interleaved gate / up weight (256-row groups = 128 gate_proj rows + the matching 128 up_proj rows);
+ * gu [M, 2I] = A W^T in that interleaved column order (kept for the backward), h [M, I] = bf16(bf16(act(gate)) * up).
+ * Bit-identical to b200_gemm_bf16 followed by b200_glu_fwd.  M > 128, I % 128 == 0; gelu: 0 SwiGLU, 1 GeGLU. */
+int b200_gemm_glu_bf16(const void* A, const void* W, void* gu, void* h, int M, int I, int K, int lda, int ldw, int ldgu,
+                       int ldh, int gelu, b200_stream_t stream);
 /* 1-CTA variant (128x256 tiles); b200_gemm_bf16 dispatches to it for M <= 128 */
 int b200_gemm_bf16_1sm(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
                        int b_mn, int accumulate, b200_stream_t stream);
@@ -64,7 +70,9 @@ int b200_rope_table(const float* inv_freq, const int64_t* position_ids, void* co
 int b200_rope(void* qkv, const void* cos_t, const void* sin_t, int B, int S, int n_rot, int D, int row_stride,
               int cos_batch, int bwd, b200_stream_t stream);
 
-/* LlamaMLP gate: act(gate) * up (models/llama/modeling_llama.py:174-176; activations.py:30-49, :92-103). */
+/* LlamaMLP gate: act(gate) * up (models/llama/modeling_llama.py:174-176; activations.py:30-49, :92-103).  `gelu` carries
+ * two flags: bit 0 = GeGLU (tanh approximation) instead of SwiGLU; bit 1 = gate / up are block-interleaved in ONE [T, 2I]
+ * matrix (256-column groups of 128 gate + 128 up columns: the layout b200_gemm_glu_bf16 writes; pass up = gate + 128). */
 int b200_glu_fwd(const void* gate, const void* up, void* out, int T, int I, int ld_gu, int ld_out, int gelu,
                  b200_stream_t stream);
 int b200_glu_bwd(const void* dh, const void* gate, const void* up, void* dgate, void* dup, int T, int I, int ld_dh,

@@ -109,20 +109,62 @@ def _act(g, gelu):
     return F.gelu(g, approximate="tanh") if gelu else F.silu(g)
 
 
-def glu_fwd(gu, gelu=False):
+GLU_BLOCK = 128
+
+
+def _halves(gu, interleaved):
+    """(gate, up) views of a [.., 2I] projection output in the plain or the 128-column block-interleaved layout."""
     I = gu.shape[-1] // 2
+    if not interleaved:
+        return gu[..., :I], gu[..., I:]
+    v = gu.reshape(*gu.shape[:-1], I // GLU_BLOCK, 2, GLU_BLOCK)
+    return v[..., 0, :].reshape(*gu.shape[:-1], I), v[..., 1, :].reshape(*gu.shape[:-1], I)
+
+
+def glu_fwd(gu, gelu=False, interleaved=False):
+    g, u = _halves(gu, interleaved)
     _log("glu_fwd", gu)
-    return _act(gu[..., :I], gelu) * gu[..., I:]
+    return _act(g, gelu) * u
 
 
-def glu_bwd(dh, gu, gelu=False):
+def glu_bwd(dh, gu, gelu=False, interleaved=False):
     with torch.enable_grad():
-        g = gu.detach().clone().requires_grad_(True)
-        I = g.shape[-1] // 2
-        y = _act(g[..., :I], gelu) * g[..., I:]
-        (dgu,) = torch.autograd.grad(y, g, dh.reshape(y.shape))
+        x = gu.detach().clone().requires_grad_(True)
+        g, u = _halves(x, interleaved)
+        y = _act(g, gelu) * u
+        (dgu,) = torch.autograd.grad(y, x, dh.reshape(y.shape))
     _log("glu_bwd", gu)
     return dgu
+
+
+def interleave_gate_up(wg, wu):
+    I, K = wg.shape
+    assert I % GLU_BLOCK == 0
+    return torch.stack([wg.reshape(I // GLU_BLOCK, GLU_BLOCK, K), wu.reshape(I // GLU_BLOCK, GLU_BLOCK, K)], dim=1).reshape(2 * I, K).contiguous()
+
+
+def deinterleave_gate_up(t):
+    n = t.shape[0] // (2 * GLU_BLOCK)
+    v = t.reshape(n, 2, GLU_BLOCK, *t.shape[1:])
+    return v[:, 0].reshape(n * GLU_BLOCK, *t.shape[1:]), v[:, 1].reshape(n * GLU_BLOCK, *t.shape[1:])
+
+
+def gemm_glu(a, w_ilv, gelu=False, gu_out=None, h_out=None):
+    gu = a @ w_ilv.t()
+    g, u = _halves(gu, True)
+    h = _act(g, gelu) * u
+    _log("gemm_glu", a, w_ilv)
+    if gu_out is not None:
+        gu_out.copy_(gu)
+        gu = gu_out
+    if h_out is not None:
+        h_out.copy_(h)
+        h = h_out
+    return gu, h
+
+
+def glu_fusable(M, I):
+    return M > 128 and I % GLU_BLOCK == 0
 
 
 def _attn_math(q, k, v, scale, causal, window, softcap, kv_start, kv_end):
@@ -427,14 +469,14 @@ class FakePeerWorkspace:
         assert src != self.rank, "own rows are a local copy"
         return self._peers_shard[src].view(rows, cols)
 
-    def copy_context(self):
+    def copy_context(self, i=0):
         return self._null()
 
     def join_copies(self):
         pass
 
 
-_NAMES = ["gemm", "embedding_fwd", "embedding_bwd", "rmsnorm_fwd", "rmsnorm_bwd", "rope_", "rope_table", "glu_fwd", "glu_bwd", "attn_fwd",
+_NAMES = ["gemm", "gemm_glu", "glu_fusable", "interleave_gate_up", "deinterleave_gate_up", "embedding_fwd", "embedding_bwd", "rmsnorm_fwd", "rmsnorm_bwd", "rope_", "rope_table", "glu_fwd", "glu_bwd", "attn_fwd",
           "attn_bwd", "ce_fwd", "ce_bwd", "ce_row_lse", "ce_bwd_sharded", "add", "kv_append", "pull_reduce", "gemm_scatter", "moe_route", "moe_gather",
           "moe_combine", "moe_experts_forward", "optim_chunk_elems",
           "adamw_step", "grad_norm", "grad_scale_"]

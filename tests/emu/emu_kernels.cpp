@@ -167,14 +167,14 @@ extern "C" int emu_rope(void* qkv, const void* c, const void* s, int B, int S, i
 }
 extern "C" int emu_glu_fwd(const void* g, const void* u, void* out, int T, int I, int ld_gu, int ld_out, int gelu) {
   emu::launch(dim3(cdiv(I / 8, 256), cdiv(T, GLU_ROWS)), dim3(256), [&] {
-    glu_fwd_kernel(reinterpret_cast<const bf*>(g), reinterpret_cast<const bf*>(u), reinterpret_cast<bf*>(out), T, I / 8, ld_gu, ld_out, gelu);
+    glu_fwd_kernel(reinterpret_cast<const bf*>(g), reinterpret_cast<const bf*>(u), reinterpret_cast<bf*>(out), T, I / 8, ld_gu, ld_out, gelu & 1, (gelu >> 1) & 1);
   });
   return 0;
 }
 extern "C" int emu_glu_bwd(const void* dh, const void* g, const void* u, void* dg, void* du, int T, int I, int ld_dh, int ld_gu, int ld_dgu, int gelu) {
   emu::launch(dim3(cdiv(I / 8, 256), cdiv(T, GLU_BWD_ROWS)), dim3(256), [&] {
     glu_bwd_kernel(reinterpret_cast<const bf*>(dh), reinterpret_cast<const bf*>(g), reinterpret_cast<const bf*>(u), reinterpret_cast<bf*>(dg),
-                   reinterpret_cast<bf*>(du), T, I / 8, ld_dh, ld_gu, ld_dgu, gelu);
+                   reinterpret_cast<bf*>(du), T, I / 8, ld_dh, ld_gu, ld_dgu, gelu & 1, (gelu >> 1) & 1);
   });
   return 0;
 }

@@ -455,3 +455,32 @@ def test_fused_head_loss_matches_stock_head_and_loss(variant, monkeypatch):
     ours.eval()
     torch.testing.assert_close(ours(input_ids=ids, labels=labels, use_cache=False).logits,
                                ref.eval()(input_ids=ids, use_cache=False).logits, atol=2e-5, rtol=1e-4)
+
+
+# ------------------------------------------------------------------------------------- GLU in the gate|up GEMM epilogue
+@pytest.mark.parametrize("kind", ["llama_silu", "gemma2_gelu"])
+def test_gate_up_glu_fused_path_matches_stock_mlp(kind):
+    """MLP widths that are whole 128-column blocks and more than one 128-row tile of tokens take the fused path: ONE launch for
+    gate|up projection + activation on the block-interleaved weight (functional.GateUpGluFn), GLU backward on the interleaved
+    layout, weight gradient de-interleaved into gate_proj / up_proj.  Everything must equal the stock model."""
+    if kind == "llama_silu":
+        ref, ours = _pair(transformers.LlamaForCausalLM, _llama_cfg(intermediate_size=384))
+    else:
+        cfg = transformers.Gemma2Config(vocab_size=160, hidden_size=64, intermediate_size=256, num_hidden_layers=2,
+                                        num_attention_heads=4, num_key_value_heads=2, head_dim=16, sliding_window=32,
+                                        query_pre_attn_scalar=16, max_position_embeddings=256,
+                                        layer_types=["sliding_attention", "full_attention"])
+        ref, ours = _pair(transformers.Gemma2ForCausalLM, cfg)
+    torch.manual_seed(7)
+    ids = torch.randint(0, 160, (2, 80))  # T = 160 > 128
+    _compare(ref, ours, ids)
+    names = [c[0] for c in _fake_ops.CALLS]
+    assert names.count("gemm_glu") == 2 and "glu_fwd" not in names and names.count("glu_bwd") == 2
+    # the interleaved copy follows parameter updates (same cache discipline as fused_weight)
+    mlp = ours.model.layers[0].mlp
+    with torch.no_grad():
+        mlp.gate_proj.weight.add_(0.01)
+        ref.model.layers[0].mlp.gate_proj.weight.add_(0.01)
+    ref.zero_grad()
+    ours.zero_grad()
+    _compare(ref, ours, ids)

@@ -311,6 +311,22 @@ def test_glu_and_add_kernels_emulated(emu2, gelu):
     c = torch.empty(T * I, dtype=BF)
     emu2.emu_add(a.data_ptr(), b.data_ptr(), c.data_ptr(), T * I)
     assert torch.equal(c, a + b)
+    # block-interleaved layout (what the GLU-epilogue GEMM writes: 256-column groups = 128 gate + 128 up columns; flag bit 1):
+    # same values, same arithmetic -> bit-identical to the plain layout
+    I2 = 2304  # 18 blocks of 128
+    gu2 = torch.randn(T, 2 * I2).to(BF)
+    ilv = gu2.view(T, 2, I2 // 128, 128).permute(0, 2, 1, 3).reshape(T, 2 * I2).contiguous()
+    plain, inter = torch.empty(T, I2, dtype=BF), torch.empty(T, I2, dtype=BF)
+    emu2.emu_glu_fwd(gu2.data_ptr(), gu2.data_ptr() + 2 * I2, plain.data_ptr(), T, I2, 2 * I2, I2, gelu)
+    emu2.emu_glu_fwd(ilv.data_ptr(), ilv.data_ptr() + 2 * 128, inter.data_ptr(), T, I2, 2 * I2, I2, gelu | 2)
+    assert torch.equal(plain, inter)
+    dh2 = torch.randn(T, I2).to(BF)
+    d_plain, d_ilv = torch.empty(T, 2 * I2, dtype=BF), torch.empty(T, 2 * I2, dtype=BF)
+    emu2.emu_glu_bwd(dh2.data_ptr(), gu2.data_ptr(), gu2.data_ptr() + 2 * I2, d_plain.data_ptr(), d_plain.data_ptr() + 2 * I2, T, I2, I2,
+                     2 * I2, 2 * I2, gelu)
+    emu2.emu_glu_bwd(dh2.data_ptr(), ilv.data_ptr(), ilv.data_ptr() + 2 * 128, d_ilv.data_ptr(), d_ilv.data_ptr() + 2 * 128, T, I2, I2,
+                     2 * I2, 2 * I2, gelu | 2)
+    assert torch.equal(d_ilv.view(T, I2 // 128, 2, 128).permute(0, 2, 1, 3).reshape(T, 2 * I2), d_plain)
 
 
 @pytest.mark.timeout(600)

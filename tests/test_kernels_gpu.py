@@ -60,6 +60,48 @@ def test_gemm_linearity_full_size():
     assert _rel(y1[:256], ref) < 1e-2
 
 
+@pytest.mark.parametrize("M,N,K", [(384, 512, 192), (2048, 4096, 1024), (300, 264, 520)])
+def test_gemm_accumulate_through_tma_reduce_add(M, N, K):
+    """accumulate=True on the CTA-pair kernel: C += A B^T leaves the SM as a TMA reduce-add of the bf16 tile (no read-modify-
+    write of C in the epilogue); repeated accumulation, M / N tails, and the MN-major (wgrad) operand layout."""
+    ops = _ops()
+    a, b = _randn(M, K, seed=11).cuda(), _randn(N, K, seed=12, scale=0.1).cuda()
+    ref = a.float() @ b.float().t()
+    c0 = _randn(M, N, seed=13).cuda()
+    c = c0.clone()
+    ops.gemm(a, b, out=c, accumulate=True)
+    assert _rel(c, ref + c0.float()) < 1e-2
+    ops.gemm(a, b, out=c, accumulate=True)
+    assert _rel(c, 2 * ref + c0.float()) < 1.5e-2
+    if M % 8 == 0 and N % 8 == 0:
+        c = c0.clone()
+        ops.gemm(a.t().contiguous(), b.t().contiguous(), a_mn=True, b_mn=True, out=c, accumulate=True)
+        assert _rel(c, ref + c0.float()) < 1e-2
+
+
+@pytest.mark.parametrize("M,I,K,gelu", [(384, 256, 192, False), (1000, 384, 520, True), (2048, 1792, 4096, False)])
+def test_gemm_glu_epilogue_is_bit_identical_to_gemm_then_glu(M, I, K, gelu):
+    """b200_gemm_glu_bf16 (gate|up projection on the block-interleaved weight + gated activation in the epilogue) vs the two
+    kernels it replaces, b200_gemm_bf16 on the concatenated weight + b200_glu_fwd: same accumulation order, same rounding
+    points -> bit-identical projections and activations; then the interleaved-layout GLU backward vs the plain one."""
+    ops = _ops()
+    x = _randn(M, K, seed=14).cuda()
+    wg, wu = _randn(I, K, seed=15, scale=0.05).cuda(), _randn(I, K, seed=16, scale=0.05).cuda()
+    gu_plain = ops.gemm(x, torch.cat([wg, wu]))
+    h_plain = ops.glu_fwd(gu_plain, gelu)
+    gu_ilv, h = ops.gemm_glu(x, ops.interleave_gate_up(wg, wu), gelu)
+    blocks = gu_ilv.view(M, I // 128, 2, 128)
+    assert torch.equal(blocks[:, :, 0].reshape(M, I), gu_plain[:, :I]) and torch.equal(blocks[:, :, 1].reshape(M, I), gu_plain[:, I:])
+    assert torch.equal(h, h_plain)
+    assert torch.equal(ops.glu_fwd(gu_ilv, gelu, interleaved=True), h_plain)
+    dh = _randn(M, I, seed=17).cuda()
+    d_plain = ops.glu_bwd(dh, gu_plain, gelu)
+    d_ilv = ops.glu_bwd(dh, gu_ilv, gelu, interleaved=True).view(M, I // 128, 2, 128)
+    assert torch.equal(d_ilv[:, :, 0].reshape(M, I), d_plain[:, :I]) and torch.equal(d_ilv[:, :, 1].reshape(M, I), d_plain[:, I:])
+    g, u = ops.deinterleave_gate_up(ops.interleave_gate_up(wg, wu))
+    assert torch.equal(g, wg) and torch.equal(u, wu)
+
+
 def test_embedding_bit_exact_and_scatter():
     ops = _ops()
     V, H = 1000, 256

@@ -26,7 +26,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, q, mode, sp, S=12, vp=False, peer=False):
+def _worker(rank, world, port, q, mode, sp, S=12, vp=False, peer=False, inter=176):
     try:
         sys.path.insert(0, ROOT)
         sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -40,7 +40,7 @@ def _worker(rank, world, port, q, mode, sp, S=12, vp=False, peer=False):
         from transformers_b200.parallel import resolve_plan, tensor_parallelize
 
         transformers_b200.enable()
-        cfg = tf.LlamaConfig(vocab_size=160, hidden_size=64, intermediate_size=176, num_hidden_layers=2, num_attention_heads=4,
+        cfg = tf.LlamaConfig(vocab_size=160, hidden_size=64, intermediate_size=inter, num_hidden_layers=2, num_attention_heads=4,
                              num_key_value_heads=2, head_dim=16, max_position_embeddings=512,
                              rope_parameters={"rope_type": "default", "rope_theta": 10000.0})
         tf.set_seed(0)
@@ -73,7 +73,7 @@ def _worker(rank, world, port, q, mode, sp, S=12, vp=False, peer=False):
         att = model.model.layers[0].self_attn
         assert att.q_proj.weight.shape == (4 * 16 // world, 64) and att.k_proj.weight.shape == (2 * 16 // world, 64)
         assert att.o_proj.weight.shape == (64, 4 * 16 // world)
-        assert model.model.layers[0].mlp.down_proj.weight.shape == (64, 176 // world)
+        assert model.model.layers[0].mlp.down_proj.weight.shape == (64, inter // world)
         assert model.lm_head.weight.shape == (160 // world, 64)
         out = model(input_ids=ids, labels=ids)
         out.loss.backward()
@@ -89,8 +89,12 @@ def _worker(rank, world, port, q, mode, sp, S=12, vp=False, peer=False):
             shapes = [c[1][0] for c in _fake_ops.CALLS if c[0] == "gemm"]
             if not sp and 2 * S >= 512:  # rowwise GEMMs (o, down) are issued in two row halves so the all-reduces overlap
                 assert sum(1 for sh in shapes if sh[0] == S) >= 2 * 2 * 2, shapes
-            if sp and not peer:  # every fused linear inside a block runs chunk by chunk: (qkv, o, gate|up, down) x (fwd, dgrad) x 3 chunks
+            if sp and not peer and S == 12:  # every fused linear inside a block runs chunk by chunk: (qkv, o, gate|up, down) x (fwd, dgrad) x 3 chunks
                 assert sum(1 for sh in shapes if sh[0] == 24 // 3) == 2 * 4 * 2 * 3, shapes
+        if mode == "kernel-path" and inter % (128 * world) == 0 and 2 * S > 128:
+            # whole 128-column blocks per rank and more than one row tile: gate|up projection + activation are ONE launch on the
+            # rank's block-interleaved weight shard (functional.GateUpGluFn), also under sequence parallelism / the peer transport
+            assert names.count("gemm_glu") >= 2 and "glu_fwd" not in names and names.count("glu_bwd") == 2
         if vp:  # labels were passed: lm_head kept its vocabulary shard and the loss exchanged per-row statistics only
             assert out.logits.shape[-1] == 160 // world and "ce_bwd_sharded" in names and "ce_fwd" not in names
             ref_logits = ref_logits.chunk(world, dim=-1)[rank]
@@ -114,16 +118,18 @@ def _worker(rank, world, port, q, mode, sp, S=12, vp=False, peer=False):
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("mode,sp,S,vp,peer", [("stock", False, 12, False, False), ("stock", True, 12, False, False),
-                                               ("kernel-path", False, 12, False, False), ("kernel-path", True, 12, True, False),
-                                               ("kernel-path", False, 256, True, False), ("kernel-path", True, 12, False, True),
-                                               ("kernel-path", True, 256, False, "scatter")])
-def test_tp2_matches_single_process_gloo(mode, sp, S, vp, peer):
+@pytest.mark.parametrize("mode,sp,S,vp,peer,inter", [("stock", False, 12, False, False, 176), ("stock", True, 12, False, False, 176),
+                                                     ("kernel-path", False, 12, False, False, 176), ("kernel-path", True, 12, True, False, 176),
+                                                     ("kernel-path", False, 256, True, False, 176), ("kernel-path", True, 12, False, True, 176),
+                                                     ("kernel-path", True, 256, False, "scatter", 176),
+                                                     ("kernel-path", False, 96, False, False, 256), ("kernel-path", True, 384, True, False, 512),
+                                                     ("kernel-path", True, 256, True, "scatter", 256)])
+def test_tp2_matches_single_process_gloo(mode, sp, S, vp, peer, inter):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q, mode, sp, S, vp, peer)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, mode, sp, S, vp, peer, inter)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=280) for _ in range(world)]

@@ -9,6 +9,8 @@
 #include <cuda_bf16.h>
 #include <math.h>
 
+#include "act.cuh"
+
 namespace b200 {
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -312,54 +314,30 @@ __global__ void rope_kernel(__nv_bfloat16* __restrict__ qkv, const __nv_bfloat16
 // ------------------------------------------------------------------------------------------------ gated MLP activation
 // reference: LlamaMLP.forward models/llama/modeling_llama.py:174-176: h = bf16( bf16(act(g)) * u )
 //   act = silu (activations.py:92-103) or gelu(approximate="tanh") (activations.py:30-49, Gemma)
-// One transcendental per element: sigmoid(g) = rcp(1 + 2^(-g*log2e)) (MUFU.EX2 + MUFU.RCP) or tanh.approx (MUFU.TANH); the
-// first version used IEEE division and recomputed the exponential for the gradient, which made glu_bwd ALU-bound
-// (~50 instructions per element, 0.46 ms of pure issue per call at the Llama-3-8B shape).
-__device__ __forceinline__ float fast_tanhf(float x) {
-#ifdef B200_HOST_EMU
-  return tanhf(x);
-#else
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-#endif
-}
-__device__ __forceinline__ void act_fwd_grad(float g, int gelu, float& act, float& dact) {
-  if (!gelu) {
-    const float s = __frcp_rn(1.0f + __expf(-g));
-    act = g * s;
-    dact = s * (1.0f + g * (1.0f - s));
-  } else {
-    const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-    const float g2 = g * g;
-    const float t = fast_tanhf(k0 * g * (1.0f + k1 * g2));
-    act = 0.5f * g * (1.0f + t);
-    dact = 0.5f * (1.0f + t) + 0.5f * g * (1.0f - t * t) * k0 * (1.0f + 3.0f * k1 * g2);
-  }
-}
-__device__ __forceinline__ float act_fwd(float g, int gelu) {
-  if (!gelu) return g * __frcp_rn(1.0f + __expf(-g));
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  return 0.5f * g * (1.0f + fast_tanhf(k0 * g * (1.0f + k1 * g * g)));
-}
-
+// The activation itself lives in act.cuh (shared with the GEMM's GLU epilogue).  The first version used IEEE division and
+// recomputed the exponential for the gradient, which made glu_bwd ALU-bound (~50 instructions per element, 0.46 ms of pure
+// issue per call at the Llama-3-8B shape).
+// Column layout: plain (gate and up are separate [T, I] matrices with a common row pitch) or BLOCK-INTERLEAVED
+// (ilv = 1: one [T, 2I] matrix whose 256-column groups hold 128 gate columns followed by the matching 128 up columns -- the
+// layout the GLU-epilogue GEMM produces, so that a 256-wide output tile carries both halves of its columns).
 // 2-D launch: blockIdx.y walks GLU_ROWS token rows, threads walk 16-byte column chunks -> no integer division per element
 // (a 64-bit div/mod per chunk made the first version ALU-bound: ncu sm__throughput 67 % at 4 TB/s).
 constexpr int GLU_ROWS = 4;
 
 __global__ void __launch_bounds__(256)
 glu_fwd_kernel(const __nv_bfloat16* __restrict__ gate, const __nv_bfloat16* __restrict__ up,
-               __nv_bfloat16* __restrict__ out, int T, int I8, int ld_gu, int ld_out, int gelu) {
+               __nv_bfloat16* __restrict__ out, int T, int I8, int ld_gu, int ld_out, int gelu, int ilv) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int t0 = blockIdx.y * GLU_ROWS;
   if (c >= I8) return;
+  const int cg = ilv ? ((c >> 4) << 5) + (c & 15) : c;  // 16-byte chunk index of gate / up column chunk c (16 chunks = 128 columns)
   uint4 gv[GLU_ROWS], uv[GLU_ROWS];
 #pragma unroll
   for (int j = 0; j < GLU_ROWS; ++j) {
     const int t = t0 + j;
     if (t < T) {
-      gv[j] = __ldg(reinterpret_cast<const uint4*>(gate + static_cast<size_t>(t) * ld_gu) + c);
-      uv[j] = __ldg(reinterpret_cast<const uint4*>(up + static_cast<size_t>(t) * ld_gu) + c);
+      gv[j] = __ldg(reinterpret_cast<const uint4*>(gate + static_cast<size_t>(t) * ld_gu) + cg);
+      uv[j] = __ldg(reinterpret_cast<const uint4*>(up + static_cast<size_t>(t) * ld_gu) + cg);
     }
   }
 #pragma unroll
@@ -370,7 +348,7 @@ glu_fwd_kernel(const __nv_bfloat16* __restrict__ gate, const __nv_bfloat16* __re
       unpack8(gv[j], g);
       unpack8(uv[j], u);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] = bf16_round(act_fwd(g[e], gelu)) * u[e];
+      for (int e = 0; e < 8; ++e) o[e] = glu_value(g[e], u[e], gelu);
       *(reinterpret_cast<uint4*>(out + static_cast<size_t>(t) * ld_out) + c) = pack8(o);
     }
   }
@@ -381,18 +359,19 @@ constexpr int GLU_BWD_ROWS = 2;
 __global__ void __launch_bounds__(256)
 glu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ gate,
                const __nv_bfloat16* __restrict__ up, __nv_bfloat16* __restrict__ dgate,
-               __nv_bfloat16* __restrict__ dup, int T, int I8, int ld_dh, int ld_gu, int ld_dgu, int gelu) {
+               __nv_bfloat16* __restrict__ dup, int T, int I8, int ld_dh, int ld_gu, int ld_dgu, int gelu, int ilv) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int t0 = blockIdx.y * GLU_BWD_ROWS;
   if (c >= I8) return;
+  const int cg = ilv ? ((c >> 4) << 5) + (c & 15) : c;
   uint4 dv[GLU_BWD_ROWS], gv[GLU_BWD_ROWS], uv[GLU_BWD_ROWS];
 #pragma unroll
   for (int j = 0; j < GLU_BWD_ROWS; ++j) {
     const int t = t0 + j;
     if (t < T) {
       dv[j] = __ldg(reinterpret_cast<const uint4*>(dh + static_cast<size_t>(t) * ld_dh) + c);
-      gv[j] = __ldg(reinterpret_cast<const uint4*>(gate + static_cast<size_t>(t) * ld_gu) + c);
-      uv[j] = __ldg(reinterpret_cast<const uint4*>(up + static_cast<size_t>(t) * ld_gu) + c);
+      gv[j] = __ldg(reinterpret_cast<const uint4*>(gate + static_cast<size_t>(t) * ld_gu) + cg);
+      uv[j] = __ldg(reinterpret_cast<const uint4*>(up + static_cast<size_t>(t) * ld_gu) + cg);
     }
   }
 #pragma unroll
@@ -410,8 +389,8 @@ glu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __rest
         du[e] = d[e] * bf16_round(a);
         dg[e] = bf16_round(d[e] * u[e]) * da;
       }
-      *(reinterpret_cast<uint4*>(dgate + static_cast<size_t>(t) * ld_dgu) + c) = pack8(dg);
-      *(reinterpret_cast<uint4*>(dup + static_cast<size_t>(t) * ld_dgu) + c) = pack8(du);
+      *(reinterpret_cast<uint4*>(dgate + static_cast<size_t>(t) * ld_dgu) + cg) = pack8(dg);
+      *(reinterpret_cast<uint4*>(dup + static_cast<size_t>(t) * ld_dgu) + cg) = pack8(du);
     }
   }
 }
@@ -687,10 +666,11 @@ extern "C" int b200_rope(void* qkv, const void* cos_t, const void* sin_t, int B,
 extern "C" int b200_glu_fwd(const void* gate, const void* up, void* out, int T, int I, int ld_gu, int ld_out, int gelu,
                             cudaStream_t stream) {
   B200_REQUIRE(I % 8 == 0 && ld_gu % 8 == 0 && ld_out % 8 == 0, "glu_fwd: I=%d must be a multiple of 8", I);
+  B200_REQUIRE(!(gelu & 2) || I % 128 == 0, "glu_fwd: the block-interleaved layout needs I=%d to be a multiple of 128", I);
   if (T == 0 || I == 0) return B200_OK;
   glu_fwd_kernel<<<dim3(ceil_div(I / 8, 256), ceil_div(T, GLU_ROWS)), 256, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(gate), reinterpret_cast<const __nv_bfloat16*>(up),
-      reinterpret_cast<__nv_bfloat16*>(out), T, I / 8, ld_gu, ld_out, gelu);
+      reinterpret_cast<__nv_bfloat16*>(out), T, I / 8, ld_gu, ld_out, gelu & 1, (gelu >> 1) & 1);
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }
@@ -698,11 +678,12 @@ extern "C" int b200_glu_fwd(const void* gate, const void* up, void* out, int T, 
 extern "C" int b200_glu_bwd(const void* dh, const void* gate, const void* up, void* dgate, void* dup, int T, int I,
                             int ld_dh, int ld_gu, int ld_dgu, int gelu, cudaStream_t stream) {
   B200_REQUIRE(I % 8 == 0 && ld_gu % 8 == 0 && ld_dh % 8 == 0 && ld_dgu % 8 == 0, "glu_bwd: I=%d must be a multiple of 8", I);
+  B200_REQUIRE(!(gelu & 2) || I % 128 == 0, "glu_bwd: the block-interleaved layout needs I=%d to be a multiple of 128", I);
   if (T == 0 || I == 0) return B200_OK;
   glu_bwd_kernel<<<dim3(ceil_div(I / 8, 256), ceil_div(T, GLU_BWD_ROWS)), 256, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(dh), reinterpret_cast<const __nv_bfloat16*>(gate),
       reinterpret_cast<const __nv_bfloat16*>(up), reinterpret_cast<__nv_bfloat16*>(dgate),
-      reinterpret_cast<__nv_bfloat16*>(dup), T, I / 8, ld_dh, ld_gu, ld_dgu, gelu);
+      reinterpret_cast<__nv_bfloat16*>(dup), T, I / 8, ld_dh, ld_gu, ld_dgu, gelu & 1, (gelu >> 1) & 1);
   B200_CHECK_CUDA(cudaGetLastError());
   return B200_OK;
 }

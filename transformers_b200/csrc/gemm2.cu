@@ -6,6 +6,7 @@
 // pipeline stages fit.  The leader CTA's single MMA thread issues tcgen05.mma.cta_group::2 for both SMs;
 // tcgen05.commit multicasts stage-release / accumulator-ready arrivals to both CTAs; the peer CTA's TMA loads complete
 // on the leader's mbarrier; the peer's epilogue warps signal "accumulator drained" on the leader's barrier remotely.
+#include "act.cuh"
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -35,9 +36,13 @@ struct Gemm2Params {
   const CUtensorMap* scatter_maps;
   int rows_per_owner;
   int m_rot;
+  // GLU variant only: the weight rows are block-interleaved (256-row groups = 128 gate rows + 128 up rows), so every
+  // 256-column output tile holds 128 gate columns and the matching 128 up columns; the epilogue stores them (tmC, the
+  // [M, 2I] interleaved gate|up matrix the backward needs) AND act(gate) * up (tmH, [M, I])
+  int gelu;
 };
 
-constexpr int G2_MODE_PLAIN = 0, G2_MODE_SCATTER = 2;
+constexpr int G2_MODE_PLAIN = 0, G2_MODE_SCATTER = 2, G2_MODE_GLU = 3;
 
 // (A soft lock-step of the persistent clusters at tile boundaries -- to keep co-running tiles walking K together and cut
 // the DRAM re-reads -- was measured in round 2: no step-time gain on the Llama-3-8B shapes, so it is gone;
@@ -45,7 +50,7 @@ constexpr int G2_MODE_PLAIN = 0, G2_MODE_SCATTER = 2;
 template <int A_MN, int B_MN, int MODE>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                      const __grid_constant__ CUtensorMap tmC, Gemm2Params p) {
+                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmH, Gemm2Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_smem = smem + G2_STAGES * G2_STAGE_BYTES;
@@ -86,6 +91,7 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   constexpr bool SCATTER = MODE == G2_MODE_SCATTER;
+  constexpr bool GLU = MODE == G2_MODE_GLU;
 
   auto tile_coords = [&](int tile, int& tm, int& tn) {
     const int group_size = p.group_m * num_n;
@@ -179,7 +185,67 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * G2_BN;
       const int ncols = min(G2_BN, p.N - tn * G2_BN);
-      {
+      if constexpr (GLU) {
+        // tile columns [0, 128) = gate, [128, 256) = up of the same 128 MLP columns (N % 256 == 0 is required).  Per 64-column
+        // chunk: gate -> tmC, up -> tmC, act(gate) * up -> tmH, three TMA stores rotating over the two staging buffers
+        uint8_t* stage = epi_smem + (warp - 2) * 8192;
+        const int row0 = tm * G2_BM + rank * 128 + q * 32;
+        int nstore = 0;
+        auto stage_and_store = [&](const uint32_t (&pk)[32], const CUtensorMap* map, int col) {
+          uint8_t* sbuf = stage + (nstore & 1) * 4096;
+          if (nstore >= 2) {  // the store issued two stores ago must have read this buffer
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+          }
+          uint8_t* srow = sbuf + lane * 128;
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            uint4 o;
+            o.x = pk[v * 4 + 0];
+            o.y = pk[v * 4 + 1];
+            o.z = pk[v * 4 + 2];
+            o.w = pk[v * 4 + 3];
+            *reinterpret_cast<uint4*>(srow + ((v ^ (lane & 7)) << 4)) = o;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(map, sbuf, col, row0);
+            tma_store_commit();
+          }
+          ++nstore;
+        };
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t g0[32], g1[32], u0[32], u1[32];
+          tmem_ld_32x32b_x32(taddr + c * 64, g0);
+          tmem_ld_32x32b_x32(taddr + c * 64 + 32, g1);
+          tmem_ld_32x32b_x32(taddr + 128 + c * 64, u0);
+          tmem_ld_32x32b_x32(taddr + 128 + c * 64 + 32, u1);
+          tmem_ld_wait();
+          uint32_t pg[32], pu[32], ph[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const uint32_t* rg = e < 16 ? g0 : g1;
+            const uint32_t* ru = e < 16 ? u0 : u1;
+            const int i = (e & 15) * 2;
+            pg[e] = pack_bf16(__uint_as_float(rg[i]), __uint_as_float(rg[i + 1]));
+            pu[e] = pack_bf16(__uint_as_float(ru[i]), __uint_as_float(ru[i + 1]));
+            // the activation sees the bf16-rounded projections, exactly like the stand-alone GLU kernel reading them back
+            const __nv_bfloat162 gb = *reinterpret_cast<const __nv_bfloat162*>(&pg[e]);
+            const __nv_bfloat162 ub = *reinterpret_cast<const __nv_bfloat162*>(&pu[e]);
+            const float2 gf = __bfloat1622float2(gb), uf = __bfloat1622float2(ub);
+            ph[e] = pack_bf16(glu_value(gf.x, uf.x, p.gelu), glu_value(gf.y, uf.y, p.gelu));
+          }
+          stage_and_store(pg, &tmC, tn * G2_BN + c * 64);
+          stage_and_store(pu, &tmC, tn * G2_BN + 128 + c * 64);
+          stage_and_store(ph, &tmH, tn * (G2_BN / 2) + c * 64);
+        }
+        tc_fence_before();
+        mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[buf]), 0));  // accumulator drained: tell the leader
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+      } else {
         // TMEM -> registers -> bf16 -> 128B-swizzled smem tile (32 rows x 64 cols) -> one TMA store per chunk: full-line
         // writes, no per-thread global stores, M / N tails clipped by the tensor map.  accumulate: the same tile goes out
         // as a TMA reduce-add (C += tile, bf16 adds performed at L2) -- no read-modify-write through the SM
@@ -241,8 +307,8 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 }
 
 template <int A_MN, int B_MN, int MODE>
-static int launch_gemm2_v(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, Gemm2Params p,
-                          cudaStream_t stream) {
+static int launch_gemm2_v(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmH,
+                          Gemm2Params p, cudaStream_t stream) {
   auto kern = gemm_bf16_tcgen05_2sm<A_MN, B_MN, MODE>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -269,15 +335,15 @@ static int launch_gemm2_v(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  B200_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, p));
+  B200_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmH, p));
   return B200_OK;
 }
 
 template <int A_MN, int B_MN>
 static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const Gemm2Params& p,
                         cudaStream_t stream) {
-  if (p.scatter_maps) return launch_gemm2_v<A_MN, B_MN, G2_MODE_SCATTER>(tmA, tmB, tmC, p, stream);
-  return launch_gemm2_v<A_MN, B_MN, G2_MODE_PLAIN>(tmA, tmB, tmC, p, stream);
+  if (p.scatter_maps) return launch_gemm2_v<A_MN, B_MN, G2_MODE_SCATTER>(tmA, tmB, tmC, tmC, p, stream);
+  return launch_gemm2_v<A_MN, B_MN, G2_MODE_PLAIN>(tmA, tmB, tmC, tmC, p, stream);
 }
 
 }  // namespace b200
@@ -315,6 +381,7 @@ static int gemm2_run(const void* A, const void* B, void* C, int M, int N, int K,
   p.scatter_maps = scatter_maps;
   p.rows_per_owner = rows_per_owner;
   p.m_rot = m_rot;
+  p.gelu = 0;
   p.group_m = 8;  // M tiles per rasterisation group (wave footprint ~ 8 x 9.25 tiles of 256x256); 4 and 16 measured no better
   const uint32_t k_lbo = 16, k_sbo = 1024, mn_lbo = 64 * G2_BK * 2, mn_sbo = 1024;
   p.a_lbo = a_mn ? mn_lbo : k_lbo;
@@ -331,6 +398,41 @@ static int gemm2_run(const void* A, const void* B, void* C, int M, int N, int K,
 extern "C" int b200_gemm_bf16_2sm(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
                                   int a_mn, int b_mn, int accumulate, cudaStream_t stream) {
   return gemm2_run(A, B, C, M, N, K, lda, ldb, ldc, a_mn, b_mn, accumulate, nullptr, 0, 0, stream);
+}
+
+// Gate|up projection with the gated activation in the epilogue (LlamaMLP.forward models/llama/modeling_llama.py:174-176,
+// first two thirds): W is the [2I, K] BLOCK-INTERLEAVED gate / up weight (256-row groups: 128 gate_proj rows followed by the
+// matching 128 up_proj rows); gu [M, 2I] receives the projections in the same interleaved column order (kept for the
+// backward), h [M, I] = bf16(bf16(act(gate)) * up).  Bit-identical to b200_gemm_bf16 + b200_glu_fwd.  Requires M > 128
+// (CTA-pair kernel) and I % 128 == 0.
+extern "C" int b200_gemm_glu_bf16(const void* A, const void* W, void* gu, void* h, int M, int I, int K, int lda, int ldw, int ldgu,
+                                  int ldh, int gelu, cudaStream_t stream) {
+  using namespace b200;
+  B200_REQUIRE(M > 128 && I > 0 && K > 0 && I % 128 == 0, "gemm_glu: needs M > 128 and I %% 128 == 0 (M=%d I=%d K=%d)", M, I, K);
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(gu) & 15) == 0 && (reinterpret_cast<uintptr_t>(h) & 15) == 0 && ldgu % 8 == 0 &&
+                   ldh % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0,
+               "gemm_glu: outputs must be 16B aligned, leading dimensions multiples of 8");
+  CUtensorMap tmA, tmB, tmC, tmH;
+  int rc;
+  if ((rc = make_tmap_2d_bf16(&tmA, A, M, K, lda, G2_BK, 128))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tmB, W, 2 * I, K, ldw, G2_BK, 128))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tmC, gu, M, 2 * I, ldgu, 64, 32))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tmH, h, M, I, ldh, 64, 32))) return rc;
+  Gemm2Params p;
+  p.C = reinterpret_cast<__nv_bfloat16*>(gu);
+  p.M = M;
+  p.N = 2 * I;
+  p.K = K;
+  p.ldc = ldgu;
+  p.accumulate = 0;
+  p.group_m = 8;
+  p.a_lbo = p.b_lbo = 16;
+  p.a_sbo = p.b_sbo = 1024;
+  p.scatter_maps = nullptr;
+  p.rows_per_owner = 0;
+  p.m_rot = 0;
+  p.gelu = gelu & 1;
+  return launch_gemm2_v<0, 0, G2_MODE_GLU>(tmA, tmB, tmC, tmH, p, stream);
 }
 
 // GEMM whose epilogue is the first half of a reduce-scatter: D = A B^T as b200_gemm_bf16, but row block r of the output

@@ -68,28 +68,36 @@ def _peer_all_gather(local2, st):
     ws.publish_shard(local2)
     full = torch.empty(rows * st.world, K, device=local2.device, dtype=local2.dtype)
     full[st.rank * rows:(st.rank + 1) * rows].copy_(local2)
-    with ws.copy_context():
-        for i in range(1, st.world):
-            src = (st.rank + i) % st.world
+    for i in range(1, st.world):
+        src = (st.rank + i) % st.world
+        with ws.copy_context(i):  # pulls from different peers on different copy engines, in parallel
             full[src * rows:(src + 1) * rows].copy_(ws.peer_shard(src, rows, K), non_blocking=True)
     ws.join_copies()
     return full
 
 
-def _sp_gather_gemm(x_local2, w, st):
+def _sp_gather_gemm(x_local2, w, st, glu=None):
     """Colwise block entry under sequence parallelism: y = all_gather(x) @ w^T with the all-gather of chunk c+1 running
-    on the communicator's stream while chunk c is in the GEMM.  Returns (x_full [T,K] -- kept for the wgrad --, y [T,N])."""
+    on the communicator's stream while chunk c is in the GEMM.  Returns (x_full [T,K] -- kept for the wgrad --, y [T,N]);
+    with ``glu`` (the GeGLU flag; w is then the block-interleaved gate|up weight) the GEMM runs the gated activation in its
+    epilogue and the result is (x_full, y, h [T, N/2])."""
     from .parallel import sp_all_gather
 
     if st.peer is not None:
         x_full = _peer_all_gather(x_local2, st)
+        if glu is not None:
+            return (x_full, *ops.gemm_glu(x_full, w, glu))
         return x_full, ops.gemm(x_full, w)
     x_full, works = sp_all_gather(x_local2, st)
     y = x_full.new_empty(x_full.shape[0], w.shape[0])
+    h = x_full.new_empty(x_full.shape[0], w.shape[0] // 2) if glu is not None else None
     for rows, work in zip(st.chunk_rows(x_full.shape[0]), works):
         work.wait()
-        ops.gemm(x_full[rows], w, out=y[rows])
-    return x_full, y
+        if glu is not None:
+            ops.gemm_glu(x_full[rows], w, glu, gu_out=y[rows], h_out=h[rows])
+        else:
+            ops.gemm(x_full[rows], w, out=y[rows])
+    return (x_full, y, h) if glu is not None else (x_full, y)
 
 
 def _sp_dgrad_scatter(dy2, w, st):
@@ -228,6 +236,60 @@ class FusedLinearFn(torch.autograd.Function):
             w_.wait()
         del keep
         return (dx, None, None, *grads_w)
+
+
+class GateUpGluFn(torch.autograd.Function):
+    """h = act(x Wg^T) * (x Wu^T) -- the first two thirds of LlamaMLP.forward (models/llama/modeling_llama.py:174-176) as ONE
+    kernel: the gate|up GEMM on the block-interleaved weight with the gated activation in its epilogue (csrc/gemm2.cu GLU
+    mode); the projections are still written (interleaved) because the backward needs them, but never read back in the
+    forward.  Backward: d(gate|up) from the GLU backward kernel on the interleaved layout, then the usual dgrad / wgrad GEMMs
+    on the interleaved weight; the weight gradient is de-interleaved into the gate_proj / up_proj gradients.
+    ``w_ilv`` is maintained by the calling module (modules.interleaved_weight); tp modes as in FusedLinearFn ("col" /
+    "col_sp"): the block-interleaving is applied to the rank's own column shard."""
+
+    @staticmethod
+    def forward(ctx, x, w_ilv, gelu, tp, wg, wu):
+        K = x.shape[-1]
+        x2 = x.reshape(-1, K)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        _, mode, st = _tp_unpack(tp)
+        I = w_ilv.shape[0] // 2
+        if mode == "col_sp":
+            x2, gu, h = _sp_gather_gemm(x2, w_ilv, st, glu=gelu)
+            out_shape = (1, x2.shape[0], I)
+        else:
+            gu, h = ops.gemm_glu(x2, w_ilv, gelu)
+            out_shape = (*x.shape[:-1], I)
+        ctx.save_for_backward(x2, w_ilv, gu)
+        ctx.cfg = (gelu, tp, x.shape)
+        return h.view(out_shape)
+
+    @staticmethod
+    def backward(ctx, dh):
+        x2, w_ilv, gu = ctx.saved_tensors
+        gelu, tp, x_shape = ctx.cfg
+        group, mode, st = _tp_unpack(tp)
+        dgu = ops.glu_bwd(dh.reshape(-1, dh.shape[-1]), gu, gelu, interleaved=True)
+        dx, work, works, keep = None, None, (), None
+        if _needs(ctx, 0):
+            if mode == "col_sp":
+                dx, works, keep = _sp_dgrad_scatter(dgu, w_ilv, st)
+            else:
+                dx = ops.gemm(dgu, w_ilv, b_mn=True)
+                if mode == "col":
+                    work = _tp_reduce_async(dx, group)  # overlaps the wgrad GEMM below
+            dx = dx.view(x_shape)
+        dwg = dwu = None
+        if _needs(ctx, 4) or _needs(ctx, 5):
+            dw = ops.gemm(dgu, x2, a_mn=True, b_mn=True)
+            dwg, dwu = ops.deinterleave_gate_up(dw)
+        if work is not None:
+            work.wait()
+        for w_ in works:
+            w_.wait()
+        del keep
+        return dx, None, None, None, (dwg if _needs(ctx, 4) else None), (dwu if _needs(ctx, 5) else None)
 
 
 class RMSNormFn(torch.autograd.Function):

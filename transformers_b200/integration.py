@@ -245,13 +245,15 @@ def _install_fused_head_loss(model: nn.Module) -> None:
 
 
 def accelerate(model: nn.Module, attn: bool = True, head_and_loss: bool = True, pack_weights: bool = False,
-               fuse_residual: bool = True, fused_head_loss: bool = True) -> nn.Module:
+               fuse_residual: bool = True, fused_head_loss: bool = True, fuse_glu: bool = True) -> nn.Module:
     """Convert an already constructed reference model in place (class swap, parameters untouched).
     ``pack_weights``: additionally make q/k/v and gate/up weights row views of one buffer (modules.pack_weights).
     ``fuse_residual`` (default): Llama / Mistral decoder layers run their residual adds on our kernels, the first fused
     with the post-attention RMSNorm (modules.B200DecoderLayerMixin); False keeps the reference's ``torch.add``.
     ``fused_head_loss`` (default): training forwards with labels run lm_head + loss chunk by chunk without materialising the
-    [T, V] logits (``_install_fused_head_loss``); False always returns logits."""
+    [T, V] logits (``_install_fused_head_loss``); False always returns logits.
+    ``fuse_glu`` (default): the MLP's gate|up projection runs the gated activation in the GEMM epilogue (one kernel,
+    functional.GateUpGluFn) whenever the shapes allow; False keeps GEMM + GLU kernel (A/B measurements)."""
     enable()
     cmap = _class_map()
     by_base = {cls.__mro__[2]: cls for cls in cmap.values()}  # (B200X, mixin, base, ...)
@@ -278,6 +280,10 @@ def accelerate(model: nn.Module, attn: bool = True, head_and_loss: bool = True, 
                 c._experts_implementation = ATTN_NAME
             except Exception:
                 c._experts_implementation_internal = ATTN_NAME
+    if not fuse_glu:
+        for mod in model.modules():
+            if isinstance(mod, M.B200MLPMixin):
+                mod.__dict__["_b200_fuse_glu"] = False
     if pack_weights:
         M.pack_weights(model)
     if fuse_residual:

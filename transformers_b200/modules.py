@@ -50,6 +50,22 @@ def fused_weight(module: nn.Module, key: str, params: list[torch.Tensor]) -> tor
     return buf
 
 
+def interleaved_weight(module: nn.Module, wg: torch.Tensor, wu: torch.Tensor) -> torch.Tensor:
+    """The [2I, K] block-interleaved gate|up weight of the GLU-epilogue GEMM (128 gate rows, the matching 128 up rows, ...),
+    cached on the module and rebuilt when either parameter is replaced or updated (same key as ``fused_weight``)."""
+    from . import ops
+
+    sig = tuple((p.data_ptr(), p._version, tuple(p.shape)) for p in (wg, wu))
+    cache = module.__dict__.setdefault("_b200_fused", {})
+    hit = cache.get("gate_up_ilv")
+    if hit is not None and hit[0] == sig:
+        return hit[1]
+    with torch.no_grad():
+        buf = ops.interleave_gate_up(wg.detach(), wu.detach())
+    cache["gate_up_ilv"] = (sig, buf)
+    return buf
+
+
 def _is_packed(buf: torch.Tensor, params: list[torch.Tensor]) -> bool:
     if buf.dim() != 2 or not buf.is_contiguous() or sum(p.shape[0] for p in params) != buf.shape[0]:
         return False
@@ -254,8 +270,17 @@ class B200MLPMixin:
         act = getattr(self.config, "hidden_act", None) or getattr(self.config, "hidden_activation", "silu")
         if act not in ("silu", "gelu_pytorch_tanh"):
             raise B200Error(f"transformers_b200: activation {act} not supported")
-        gu = Fn.FusedLinearFn.apply(x, fused_weight(self, "gate_up", [wg, wu]), col, wg, wu)
-        h = Fn.GluFn.apply(gu, act == "gelu_pytorch_tanh")
+        gelu = act == "gelu_pytorch_tanh"
+        sp = _sp_state(self)
+        tokens = (sp.full_shape[0] * sp.full_shape[1]) if sp is not None else x.numel() // x.shape[-1]
+        from . import ops
+
+        if self.__dict__.get("_b200_fuse_glu", True) and ops.glu_fusable(tokens, wg.shape[0]) and x.dtype in KERNEL_DTYPES:
+            # gate|up GEMM with the gated activation in its epilogue: one kernel, the projections are never read back
+            h = Fn.GateUpGluFn.apply(x, interleaved_weight(self, wg, wu), gelu, col, wg, wu)
+        else:
+            gu = Fn.FusedLinearFn.apply(x, fused_weight(self, "gate_up", [wg, wu]), col, wg, wu)
+            h = Fn.GluFn.apply(gu, gelu)
         return Fn.FusedLinearFn.apply(h, fused_weight(self, "down", [wd]), row, wd)  # row mode: all-reduce inside, overlapped
 
 

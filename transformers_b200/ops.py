@@ -81,6 +81,48 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     return out
 
 
+GLU_BLOCK = 128  # column block of the interleaved gate|up layout (half of the GEMM's 256-column tile)
+
+
+def interleave_gate_up(wg: torch.Tensor, wu: torch.Tensor) -> torch.Tensor:
+    """[I, K] gate and up weights -> [2I, K] with 128-row blocks alternating gate / up (what b200_gemm_glu_bf16 expects)."""
+    I, K = wg.shape
+    if wu.shape != wg.shape or I % GLU_BLOCK:
+        raise B200Error(f"interleave_gate_up: shapes {tuple(wg.shape)} / {tuple(wu.shape)}, I must be a multiple of {GLU_BLOCK}")
+    return torch.stack([wg.reshape(I // GLU_BLOCK, GLU_BLOCK, K), wu.reshape(I // GLU_BLOCK, GLU_BLOCK, K)], dim=1).reshape(2 * I, K).contiguous()
+
+
+def deinterleave_gate_up(t: torch.Tensor):
+    """Inverse on the leading dimension: [2I, ...] interleaved rows -> (gate [I, ...], up [I, ...])."""
+    n = t.shape[0] // (2 * GLU_BLOCK)
+    v = t.reshape(n, 2, GLU_BLOCK, *t.shape[1:])
+    return v[:, 0].reshape(n * GLU_BLOCK, *t.shape[1:]), v[:, 1].reshape(n * GLU_BLOCK, *t.shape[1:])
+
+
+def gemm_glu(a: torch.Tensor, w_ilv: torch.Tensor, gelu: bool = False, gu_out: torch.Tensor | None = None,
+             h_out: torch.Tensor | None = None):
+    """a [M, K] @ block-interleaved gate|up weight [2I, K] -> (gu [M, 2I] interleaved columns, h [M, I] = act(gate) * up);
+    one kernel: the activation runs in the GEMM's epilogue (csrc/gemm2.cu GLU mode)."""
+    lib = _lib_ready()
+    _chk_bf16(a, w_ilv, gu_out, h_out)
+    M, K = a.shape
+    I = w_ilv.shape[0] // 2
+    if a.stride(1) != 1 or w_ilv.stride(1) != 1 or w_ilv.shape[1] != K:
+        raise B200Error("gemm_glu: operands must be 2-D with unit inner stride and matching contraction")
+    gu = gu_out if gu_out is not None else torch.empty(M, 2 * I, device=a.device, dtype=BF16)
+    h = h_out if h_out is not None else torch.empty(M, I, device=a.device, dtype=BF16)
+    if gu.shape != (M, 2 * I) or h.shape != (M, I) or gu.stride(1) != 1 or h.stride(1) != 1:
+        raise B200Error("gemm_glu: bad output tensors")
+    check(lib.b200_gemm_glu_bf16(a.data_ptr(), w_ilv.data_ptr(), gu.data_ptr(), h.data_ptr(), M, I, K, a.stride(0), w_ilv.stride(0),
+                                 gu.stride(0), h.stride(0), int(gelu), _stream()), "b200_gemm_glu_bf16")
+    return gu, h
+
+
+def glu_fusable(M: int, I: int) -> bool:
+    """Shapes the GLU-epilogue GEMM takes (CTA-pair kernel: more than one 128-row tile; whole 128-column blocks)."""
+    return M > 128 and I % GLU_BLOCK == 0
+
+
 # ------------------------------------------------------------------------------------------------------ embedding
 def embedding_fwd(ids: torch.Tensor, weight: torch.Tensor, scale: float | None = None) -> torch.Tensor:
     lib = _lib_ready()
@@ -191,20 +233,22 @@ def rope_(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, n_rot_heads: 
 
 
 # ------------------------------------------------------------------------------------------------------------ GLU
-def glu_fwd(gu: torch.Tensor, gelu: bool = False) -> torch.Tensor:
-    """gu [..., 2I] = [gate | up]  ->  act(gate) * up  [..., I]"""
+def glu_fwd(gu: torch.Tensor, gelu: bool = False, interleaved: bool = False) -> torch.Tensor:
+    """gu [..., 2I] = [gate | up] (``interleaved``: 128-column blocks alternating gate / up)  ->  act(gate) * up  [..., I]"""
     lib = _lib_ready()
     _chk_bf16(gu)
     I = gu.shape[-1] // 2
     g2 = gu.reshape(-1, 2 * I)
     T = g2.shape[0]
     out = torch.empty(T, I, device=gu.device, dtype=BF16)
-    check(lib.b200_glu_fwd(g2.data_ptr(), g2.data_ptr() + 2 * I, out.data_ptr(), T, I, g2.stride(0), I, int(gelu), _stream()),
-          "b200_glu_fwd")
+    up_off = 2 * (GLU_BLOCK if interleaved else I)  # bytes from the gate pointer to the up pointer
+    check(lib.b200_glu_fwd(g2.data_ptr(), g2.data_ptr() + up_off, out.data_ptr(), T, I, g2.stride(0), I,
+                           int(gelu) | (2 if interleaved else 0), _stream()), "b200_glu_fwd")
     return out.view(*gu.shape[:-1], I)
 
 
-def glu_bwd(dh: torch.Tensor, gu: torch.Tensor, gelu: bool = False) -> torch.Tensor:
+def glu_bwd(dh: torch.Tensor, gu: torch.Tensor, gelu: bool = False, interleaved: bool = False) -> torch.Tensor:
+    """d(gate|up) in the layout of ``gu`` (plain halves or interleaved 128-column blocks)."""
     lib = _lib_ready()
     I = gu.shape[-1] // 2
     g2 = gu.reshape(-1, 2 * I)
@@ -213,8 +257,9 @@ def glu_bwd(dh: torch.Tensor, gu: torch.Tensor, gelu: bool = False) -> torch.Ten
         d2 = d2.contiguous()
     T = g2.shape[0]
     dgu = torch.empty(T, 2 * I, device=gu.device, dtype=BF16)
-    check(lib.b200_glu_bwd(d2.data_ptr(), g2.data_ptr(), g2.data_ptr() + 2 * I, dgu.data_ptr(), dgu.data_ptr() + 2 * I, T, I,
-                           I, g2.stride(0), 2 * I, int(gelu), _stream()), "b200_glu_bwd")
+    up_off = 2 * (GLU_BLOCK if interleaved else I)
+    check(lib.b200_glu_bwd(d2.data_ptr(), g2.data_ptr(), g2.data_ptr() + up_off, dgu.data_ptr(), dgu.data_ptr() + up_off, T, I,
+                           I, g2.stride(0), 2 * I, int(gelu) | (2 if interleaved else 0), _stream()), "b200_glu_bwd")
     return dgu.view(gu.shape)
 
 
@@ -234,6 +279,11 @@ def _bsh_strides(t: torch.Tensor):
     if t.stride(3) != 1:
         raise B200Error("attention operands need a unit stride on head_dim")
     return t.stride(0), t.stride(1), t.stride(2)
+
+
+# A/B switch for measurements (bench.py --attn-one-tile 1): run every forward on the one-tile kernel instead of letting
+# b200_attn_fwd pick the two-tile ping-pong kernel for Sq > 128
+ATTN_ONE_TILE = False
 
 
 def _lse_stride(sq: int) -> int:
@@ -264,7 +314,7 @@ def attn_fwd(q, k, v, *, scale: float, causal: bool, window: int = 0, softcap: f
                                    kv_start.data_ptr() if kv_start is not None else None,
                                    kv_end.data_ptr() if kv_end is not None else None, _stream()), "b200_attn_decode")
         return out, lse
-    entry = lib.b200_attn_fwd_1tile if one_tile_kernel else lib.b200_attn_fwd
+    entry = lib.b200_attn_fwd_1tile if (one_tile_kernel or ATTN_ONE_TILE) else lib.b200_attn_fwd
     check(entry(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(), ls, B, Sq, Skv, Hq, Hkv, D,
                             *_bsh_strides(q), *_bsh_strides(k), *_bsh_strides(v), *_bsh_strides(out), float(scale),
                             float(softcap or 0.0), int(causal), int(window or 0),

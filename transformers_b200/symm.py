@@ -12,8 +12,9 @@ Protocol (one device-side barrier per collective, no per-message flags): op j us
 A rank can only overwrite pair j % 2 again in op j + 2, i.e. after barrier_{j+1}; every peer issued its op-j reads before
 arriving at barrier_{j+1} (stream order), so the write-after-read hazard is covered by the same barriers.
 
-Written after round 1's GPU budget was spent: exercised on CPU through ``tests/_fake_ops.py`` / a gloo stand-in for the peer
-mapping (tests/test_tp_gloo.py); to be validated on NVLink with tests/cuda/round2_validate.sh before it becomes a default.
+Validated on NVLink in round 2 (NCCL-free parity at 2 and 8 GPUs with tests/cuda/tp_check.py, profiles/r02_call2.log and
+profiles/r02_call3_tp8.log) and the default transport of ``bench.py`` for N > 1; the CPU suite exercises the same host logic
+through ``tests/_fake_ops.py`` and a gloo stand-in for the peer mapping (tests/test_tp_gloo.py).
 """
 from __future__ import annotations
 
@@ -35,7 +36,7 @@ class PeerWorkspace:
         self._shard = [None, None]
         self._j_partial = 0
         self._j_shard = 0
-        self.copy_stream = None
+        self.copy_streams = []
 
     # ------------------------------------------------------------------------------------------------ allocation
     def _alloc(self, elems: int):
@@ -53,8 +54,10 @@ class PeerWorkspace:
         self._partial = [self._alloc(elems), self._alloc(elems)]
         self._shard = [self._alloc((elems + self.world - 1) // self.world), self._alloc((elems + self.world - 1) // self.world)]
         self._elems = elems
-        if self.copy_stream is None:
-            self.copy_stream = torch.cuda.Stream(device=self.device)
+        if not self.copy_streams:
+            # several side streams: the pulls from different peers run on different copy engines in parallel (one stream
+            # serialises them: 7 x 16.7 MB at single-engine speed per all-gather at N = 8)
+            self.copy_streams = [torch.cuda.Stream(device=self.device) for _ in range(min(4, max(1, self.world - 1)))]
 
     # ---------------------------------------------------------------------------------------- reduce-scatter side
     def next_partial(self, rows: int, cols: int) -> torch.Tensor:
@@ -96,11 +99,15 @@ class PeerWorkspace:
         """[rows, cols] view of rank ``src``'s published shard (peer memory; valid until the op after next)."""
         return self._shard[self._j_shard % 2][1].get_buffer(src, (rows, cols), torch.bfloat16)
 
-    def copy_context(self):
-        """Side stream for the copy-engine pulls (waits for everything issued so far on the current stream)."""
-        self.copy_stream.wait_stream(torch.cuda.current_stream())
-        return torch.cuda.stream(self.copy_stream)
+    def copy_context(self, i: int = 0):
+        """Side stream ``i`` (round-robin over the copy streams) for a copy-engine pull; it first waits for everything issued
+        so far on the current stream (the barrier included)."""
+        st = self.copy_streams[i % len(self.copy_streams)]
+        st.wait_stream(torch.cuda.current_stream())
+        return torch.cuda.stream(st)
 
     def join_copies(self) -> None:
         """The current stream waits for the pulls issued inside ``copy_context``."""
-        torch.cuda.current_stream().wait_stream(self.copy_stream)
+        cur = torch.cuda.current_stream()
+        for st in self.copy_streams:
+            cur.wait_stream(st)
