@@ -193,6 +193,9 @@ def enable(patch_modules: bool = True) -> None:
         from transformers.monkey_patching import register_patch_mapping
 
         register_patch_mapping(_class_map(), overwrite=True)
+    from .tp_styles import register_tp_styles
+
+    register_tp_styles()  # "b200_colwise" / "b200_rowwise" / "b200_colwise_gather_output" in the reference's ParallelInterface
     _enabled = True
 
 

@@ -407,9 +407,22 @@ def _sp_state(module):
     return st if st is not None and st.active else None
 
 
+def _tp_group(module):
+    """Process group this block reduces over: set by parallel.tensor_parallelize, or -- when the model was sharded through the
+    reference's own dispatch with the styles of tp_styles.py -- found on the block's rowwise Linear."""
+    group = module.__dict__.get("_b200_tp_group")
+    if group is None:
+        for child in ("o_proj", "down_proj"):
+            lin = module.__dict__.get("_modules", {}).get(child)
+            if lin is not None and "_b200_tp_group" in lin.__dict__:
+                group = module.__dict__["_b200_tp_group"] = lin.__dict__["_b200_tp_group"]
+                break
+    return group
+
+
 def _tp_modes(module):
     """(col, row, sp) descriptors for FusedLinearFn / QKVRopeAttentionFn: ``(group, mode[, sp_state])`` or None."""
-    group = module.__dict__.get("_b200_tp_group")
+    group = _tp_group(module)
     if group is None:
         return None, None, None
     sp = _sp_state(module)
@@ -419,7 +432,7 @@ def _tp_modes(module):
 
 
 def _tp_copy(module, x):
-    group = module.__dict__.get("_b200_tp_group")
+    group = _tp_group(module)
     if group is None:
         return x
     from . import parallel
@@ -429,7 +442,7 @@ def _tp_copy(module, x):
 
 
 def _tp_allreduce(module, out):
-    group = module.__dict__.get("_b200_tp_group")
+    group = _tp_group(module)
     if group is None:
         return out
     from . import parallel
