@@ -90,13 +90,6 @@ int b200_attn_fwd(const void* q, const void* k, const void* v, void* out, float*
                   int64_t k_hs, int64_t v_bs, int64_t v_rs, int64_t v_hs, int64_t o_bs, int64_t o_rs, int64_t o_hs,
                   float scale, float softcap, int causal, int window, const int* kv_start, const int* kv_end,
                   b200_stream_t stream);
-/* same contract, always on the one-tile kernel (one 128-row q tile per CTA, two CTAs per SM) that b200_attn_fwd itself uses
- * for Sq <= 128 and head_dim 256; larger shapes go to the two-tile ping-pong kernel.  Exported for A/B timing and parity. */
-int b200_attn_fwd_1tile(const void* q, const void* k, const void* v, void* out, float* lse, int lse_stride, int B, int Sq,
-                        int Skv, int Hq, int Hkv, int D, int64_t q_bs, int64_t q_rs, int64_t q_hs, int64_t k_bs, int64_t k_rs,
-                        int64_t k_hs, int64_t v_bs, int64_t v_rs, int64_t v_hs, int64_t o_bs, int64_t o_rs, int64_t o_hs,
-                        float scale, float softcap, int causal, int window, const int* kv_start, const int* kv_end,
-                        b200_stream_t stream);
 /* strides: 8 tensors x (batch, row, head) for q, k, v, out, dout, dq, dk, dv; workspace fp32[2*B*Hq*lse_stride] */
 int b200_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse,
                   void* dq, void* dk, void* dv, float* workspace, int B, int Sq, int Skv, int Hq, int Hkv, int D,

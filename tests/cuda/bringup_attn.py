@@ -39,9 +39,9 @@ def make_qkv(B, Sq, Skv, Hq, Hkv, D, packed, g):
         v = torch.randn(B, Skv, Hkv, D, device=dev, generator=g).to(torch.bfloat16)
     return q, k, v
 
-def call_fwd(q, k, v, out, lse, causal, window, softcap, ks=None, ke=None, one_tile=False):
+def call_fwd(q, k, v, out, lse, causal, window, softcap, ks=None, ke=None):
     B, Sq, Hq, D = q.shape; Skv, Hkv = k.shape[1], k.shape[2]
-    return (lib.b200_attn_fwd_1tile if one_tile else lib.b200_attn_fwd)(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(), lse.shape[-1], B, Sq, Skv, Hq, Hkv, D,
+    return lib.b200_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(), lse.shape[-1], B, Sq, Skv, Hq, Hkv, D,
                              q.stride(0), q.stride(1), q.stride(2), k.stride(0), k.stride(1), k.stride(2), v.stride(0), v.stride(1), v.stride(2),
                              out.stride(0), out.stride(1), out.stride(2), D ** -0.5, softcap, causal, window,
                              ks.data_ptr() if ks is not None else None, ke.data_ptr() if ke is not None else None, st())
@@ -117,25 +117,7 @@ try:
     for _ in range(10): f()
     e1.record(); torch.cuda.synchronize(); ms = e0.elapsed_time(e1) / 10
     fl = 4.0 * B * Hq * S * S * D / 2
-    log(f"attn fwd B4 S4096 H32/8 D128 causal (two-tile ping-pong kernel): {ms:.3f} ms = {fl/ms/1e9:.0f} TF/s")
-    out1 = torch.empty_like(out); lse1 = torch.empty_like(lse)
-    f1 = lambda: call_fwd(q, k, v, out1, lse1, 1, 0, 0.0, one_tile=True)
-    for _ in range(3): f1()
-    torch.cuda.synchronize(); e0.record()
-    for _ in range(10): f1()
-    e1.record(); torch.cuda.synchronize(); ms1 = e0.elapsed_time(e1) / 10
-    log(f"attn fwd same shape, one-tile kernel: {ms1:.3f} ms = {fl/ms1/1e9:.0f} TF/s; max |out2 - out1| = {(out.float() - out1.float()).abs().max().item():.5f}, max |lse2 - lse1| = {(lse - lse1).abs().max().item():.6f}")
-    for (b_, s_, w_) in ((2, 8192, 0), (4, 4096, 1024), (8, 2048, 0), (1, 16384, 0)):
-        q2, k2, v2 = make_qkv(b_, s_, s_, Hq, Hkv, D, True, torch.Generator(device=dev).manual_seed(2))
-        o2 = torch.empty(b_, s_, Hq, D, device=dev, dtype=torch.bfloat16); l2 = torch.empty(b_, Hq, s_, device=dev, dtype=torch.float32)
-        res = []
-        for one in (False, True):
-            fn = lambda: call_fwd(q2, k2, v2, o2, l2, 1, w_, 0.0, one_tile=one)
-            for _ in range(2): fn()
-            torch.cuda.synchronize(); e0.record()
-            for _ in range(5): fn()
-            e1.record(); torch.cuda.synchronize(); res.append(e0.elapsed_time(e1) / 5)
-        log(f"attn fwd B{b_} S{s_} window {w_}: two-tile {res[0]:.3f} ms, one-tile {res[1]:.3f} ms")
+    log(f"attn fwd B4 S4096 H32/8 D128 causal: {ms:.3f} ms = {fl/ms/1e9:.0f} TF/s")
     for _ in range(3): fb()
     torch.cuda.synchronize(); e0.record()
     for _ in range(10): fb()

@@ -40,7 +40,6 @@ SIGNATURES = {
     "b200_moe_combine": [_p, _p, _p, _p, _i, _i, _i, _p],
     "b200_ce_fwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _l, _f, _p],
     "b200_attn_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i] + [_l] * 12 + [_f, _f, _i, _i, _p, _p, _p],
-    "b200_attn_fwd_1tile": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i] + [_l] * 12 + [_f, _f, _i, _i, _p, _p, _p],
     "b200_attn_decode_splits": [_i, _i, _i],
     "b200_attn_decode": [_p, _p, _p, _p, _p, _i, _p, _i, _i, _i, _i, _i] + [_l] * 10 + [_f, _f, _i, _p, _p, _p],
     "b200_attn_bwd": [_p] * 10 + [_i] * 7 + [_p, _f, _f, _i, _i, _p, _p, _p],

@@ -281,17 +281,12 @@ def _bsh_strides(t: torch.Tensor):
     return t.stride(0), t.stride(1), t.stride(2)
 
 
-# A/B switch for measurements (bench.py --attn-one-tile 1): run every forward on the one-tile kernel instead of letting
-# b200_attn_fwd pick the two-tile ping-pong kernel for Sq > 128
-ATTN_ONE_TILE = False
-
-
 def _lse_stride(sq: int) -> int:
     return (sq + 127) // 128 * 128
 
 
 def attn_fwd(q, k, v, *, scale: float, causal: bool, window: int = 0, softcap: float = 0.0, kv_start=None, kv_end=None,
-             out: torch.Tensor | None = None, decode_kernel: bool | None = None, one_tile_kernel: bool = False):
+             out: torch.Tensor | None = None, decode_kernel: bool | None = None):
     """q [B,Sq,Hq,D], k/v [B,Skv,Hkv,D] strided views -> (out [B,Sq,Hq,D], lse [B,Hq,lse_stride] fp32).
     q_len == 1 goes to the split-context decode kernels (``decode_kernel=False`` forces the tensor-core kernel: tests)."""
     lib = _lib_ready()
@@ -314,8 +309,7 @@ def attn_fwd(q, k, v, *, scale: float, causal: bool, window: int = 0, softcap: f
                                    kv_start.data_ptr() if kv_start is not None else None,
                                    kv_end.data_ptr() if kv_end is not None else None, _stream()), "b200_attn_decode")
         return out, lse
-    entry = lib.b200_attn_fwd_1tile if (one_tile_kernel or ATTN_ONE_TILE) else lib.b200_attn_fwd
-    check(entry(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(), ls, B, Sq, Skv, Hq, Hkv, D,
+    check(lib.b200_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(), ls, B, Sq, Skv, Hq, Hkv, D,
                             *_bsh_strides(q), *_bsh_strides(k), *_bsh_strides(v), *_bsh_strides(out), float(scale),
                             float(softcap or 0.0), int(causal), int(window or 0),
                             kv_start.data_ptr() if kv_start is not None else None,
