@@ -21,7 +21,10 @@ if want("gemm"):
     dy = rn(T, 2 * I)
     for _ in range(reps): dx = ops.gemm(dy, w, b_mn=True)          # dgrad         [NN]
     for _ in range(reps): dw = ops.gemm(dy, x, a_mn=True, b_mn=True)  # wgrad      [TT]
-    del x, w, y, dy, dx, dw
+    for _ in range(reps): ops.gemm(dy, x, a_mn=True, b_mn=True, out=dw, accumulate=True)  # wgrad, TMA reduce-add epilogue
+    w_ilv = ops.interleave_gate_up(w[:I], w[I:])
+    for _ in range(reps): gu, h = ops.gemm_glu(x, w_ilv)          # fwd gate|up with the GLU epilogue
+    del x, w, y, dy, dx, dw, w_ilv, gu, h
 if want("attn"):
     qkv = rn(B, S, (Hq + 2 * Hkv) * D)
     q = qkv[..., : Hq * D].view(B, S, Hq, D); k = qkv[..., Hq * D:(Hq + Hkv) * D].view(B, S, Hkv, D); v = qkv[..., (Hq + Hkv) * D:].view(B, S, Hkv, D)
@@ -43,7 +46,11 @@ if want("elementwise"):
     ids = torch.randint(0, 128256, (B, S), device=dev); emb = rn(128256, H)
     for _ in range(reps): e = ops.embedding_fwd(ids, emb)
     for _ in range(reps): ops.add(x, y)
-    del gu, h, qkv, emb, e
+    inv = torch.rand(D // 2, device=dev); pos = torch.arange(S, device=dev)[None]
+    for _ in range(reps): ops.rope_table(inv, pos)
+    gi = rn(T, 2 * I)
+    for _ in range(reps): ops.glu_bwd(h, gi, interleaved=True)
+    del gu, h, qkv, emb, e, gi
 if want("ce"):
     logits = rn(B, S, 128256); labels = torch.randint(0, 128256, (B, S), device=dev)
     for _ in range(reps): loss, lse, denom = ops.ce_fwd(logits, labels)

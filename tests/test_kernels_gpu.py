@@ -102,6 +102,27 @@ def test_gemm_glu_epilogue_is_bit_identical_to_gemm_then_glu(M, I, K, gelu):
     assert torch.equal(g, wg) and torch.equal(u, wu)
 
 
+def test_rope_table_bit_exact_vs_reference_ops():
+    """b200_rope_table vs LlamaRotaryEmbedding.forward's six torch ops (models/llama/modeling_llama.py:113-127) run on the same
+    device: fp32 outer product, cat, cos / sin, scale, cast -- bit for bit; and within one bf16 ulp of the CPU oracle."""
+    ops = _ops()
+    cfg = O.DecoderConfig(vocab_size=8, hidden_size=64, intermediate_size=64, num_hidden_layers=1, num_attention_heads=1,
+                          num_key_value_heads=1, head_dim=128, rope_theta=500000.0)
+    inv_freq = O.rope_inv_freq(cfg)
+    pos = torch.stack([torch.arange(4096), torch.arange(4096) + 3000])  # two rows, large angles included
+    for scaling in (1.0, 0.8333):
+        cos, sin = ops.rope_table(inv_freq.cuda(), pos.cuda(), scaling)
+        want_cos, want_sin = O.rope_tables(inv_freq.cuda(), pos.cuda(), BF, attention_scaling=scaling)
+        # same arithmetic in the same order (cosf / sinf are what torch's CUDA cos / sin call); allow a handful of elements whose
+        # fp32 value sits on a bf16 rounding boundary in case the two toolkits' libdevice differ in the last fp32 bit
+        for got, want in ((cos, want_cos), (sin, want_sin)):
+            bad = (got != want).sum().item()
+            assert bad <= 1e-4 * got.numel(), f"{bad} of {got.numel()} table entries differ from the reference's ops"
+            assert (got.float() - want.float()).abs().max() <= 2 ** -7
+        cpu_cos, cpu_sin = O.rope_tables(inv_freq, pos, BF, attention_scaling=scaling)
+        assert (cos.cpu().float() - cpu_cos.float()).abs().max() <= 2 ** -7 and (sin.cpu().float() - cpu_sin.float()).abs().max() <= 2 ** -7
+
+
 def test_embedding_bit_exact_and_scatter():
     ops = _ops()
     V, H = 1000, 256

@@ -376,7 +376,9 @@ static int launch_attn_fwd_v(const CUtensorMap& tq, const CUtensorMap& tk, const
 // tile's MMAs: bit-identical results, 0.587 ms against this kernel's 0.574 ms at B4 S4096 32/8 heads and 10 % slower inside the
 // power-capped training step (profiles/r02_attn_two_tile_vs_one_tile.txt).  The overlap was never the limit: with one thread
 // per row both tiles' softmax phases run at the same time and share the SM's 16 MUFU lanes, ~3800 cycles per tile against
-// 1048 cycles of MMA.  The variant is gone; the next lever is the exponential itself (packed bf16x2 ex2 / FMA-pipe polynomial).)
+// 1048 cycles of MMA.  The variant is gone; the next lever is the exponential itself.  ex2.approx.ftz.bf16x2 is not it: nvcc 12.9
+// lowers it to TWO MUFU.EX2.BF16 (one per half) on sm_100a, so the MUFU load is unchanged; what remains is moving part of the
+// exponentials to an FMA-pipe polynomial with packed f32x2 arithmetic.)
 template <int D, bool SOFTCAP>
 static int launch_attn_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnFwdParams& p,
                            cudaStream_t stream) {
