@@ -40,6 +40,13 @@ int b200_gemm_bf16_2sm(const void* A, const void* B, void* C, int M, int N, int 
  * Bit-identical to b200_gemm_bf16 followed by b200_glu_fwd.  M > 128, I % 128 == 0; gelu: 0 SwiGLU, 1 GeGLU. */
 int b200_gemm_glu_bf16(const void* A, const void* W, void* gu, void* h, int M, int I, int K, int lda, int ldw, int ldgu,
                        int ldh, int gelu, b200_stream_t stream);
+/* grouped GEMM for mixture-of-experts blocks (MixtralExperts.forward models/mixtral/modeling_mixtral.py:69-93;
+ * grouped_mm_experts_forward integrations/moe.py:377-478): rows [offsets[g], offsets[g+1]) of A [M_total, K] x expert g's
+ * matrix (B + g*N*K: [N, K]; b_mn: [K, N], the dgrad layout) -> the same rows of C [M_total, N].  `offsets`: int32[groups+1]
+ * in DEVICE memory (b200_moe_route's output): one launch for all experts, no host synchronisation.  groups <= 64,
+ * N % 64 == 0, b_mn needs K % 64 == 0. */
+int b200_gemm_bf16_grouped(const void* A, const void* B, void* C, const int* offsets, int groups, int M_total, int N, int K,
+                           int lda, int ldb, int ldc, int b_mn, b200_stream_t stream);
 /* 1-CTA variant (128x256 tiles); b200_gemm_bf16 dispatches to it for M <= 128 */
 int b200_gemm_bf16_1sm(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, int a_mn,
                        int b_mn, int accumulate, b200_stream_t stream);

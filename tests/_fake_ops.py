@@ -167,6 +167,25 @@ def glu_fusable(M, I):
     return M > 128 and I % GLU_BLOCK == 0
 
 
+def gemm_grouped(a, b, offsets, *, b_mn=False, out=None):
+    assert offsets.dtype == torch.int32 and offsets.numel() == b.shape[0] + 1
+    N = b.shape[2] if b_mn else b.shape[1]
+    if out is None:
+        out = a.new_zeros(a.shape[0], N)
+    off = offsets.tolist()
+    for g in range(b.shape[0]):
+        lo, hi = off[g], off[g + 1]
+        if hi > lo:
+            out[lo:hi] = a[lo:hi] @ (b[g] if b_mn else b[g].t())
+    _log("gemm_grouped", a, b)
+    return out
+
+
+def grouped_ok(gate_up, down):
+    E, I2, H = gate_up.shape
+    return E <= 64 and I2 % 64 == 0 and H % 64 == 0 and down.shape[2] % 64 == 0
+
+
 def _attn_math(q, k, v, scale, causal, window, softcap, kv_start, kv_end):
     B, Sq, Hq, D = q.shape
     Skv, Hkv = k.shape[1], k.shape[2]
@@ -476,7 +495,7 @@ class FakePeerWorkspace:
         pass
 
 
-_NAMES = ["gemm", "gemm_glu", "glu_fusable", "interleave_gate_up", "deinterleave_gate_up", "embedding_fwd", "embedding_bwd", "rmsnorm_fwd", "rmsnorm_bwd", "rope_", "rope_table", "glu_fwd", "glu_bwd", "attn_fwd",
+_NAMES = ["gemm", "gemm_grouped", "grouped_ok", "gemm_glu", "glu_fusable", "interleave_gate_up", "deinterleave_gate_up", "embedding_fwd", "embedding_bwd", "rmsnorm_fwd", "rmsnorm_bwd", "rope_", "rope_table", "glu_fwd", "glu_bwd", "attn_fwd",
           "attn_bwd", "ce_fwd", "ce_bwd", "ce_row_lse", "ce_bwd_sharded", "add", "kv_append", "pull_reduce", "gemm_scatter", "moe_route", "moe_gather",
           "moe_combine", "moe_experts_forward", "optim_chunk_elems",
           "adamw_step", "grad_norm", "grad_scale_"]

@@ -273,10 +273,13 @@ def test_make_cache_inplace_sliding_generates_like_the_reference_cache():
     torch.testing.assert_close(torch.cat(outs, 1), full, atol=5e-5, rtol=1e-4)
 
 
-def test_mixtral_moe_forward_and_backward_through_the_experts_registry():
+@pytest.mark.parametrize("inter", [96, 128])
+def test_mixtral_moe_forward_and_backward_through_the_experts_registry(inter):
     """config 4 family: the b200 experts entry (ExpertsInterface) under autograd = functional.MoEExpertsFn; gradients of the
-    hidden states, the router (through top_k_weights) and the stacked expert weights vs the stock eager experts."""
-    cfg = transformers.MixtralConfig(vocab_size=160, hidden_size=64, intermediate_size=96, num_hidden_layers=2,
+    hidden states, the router (through top_k_weights) and the stacked expert weights vs the stock eager experts.  Widths in
+    whole 64-column chunks (inter = 128) take the grouped GEMM (expert row ranges stay on the device: one launch per
+    projection, forward and dgrad); odd widths (inter = 96) the per-expert launches."""
+    cfg = transformers.MixtralConfig(vocab_size=160, hidden_size=64, intermediate_size=inter, num_hidden_layers=2,
                                      num_attention_heads=4, num_key_value_heads=2, head_dim=16, num_local_experts=4,
                                      num_experts_per_tok=2, max_position_embeddings=128, sliding_window=None,
                                      router_jitter_noise=0.0, output_router_logits=False)
@@ -287,6 +290,7 @@ def test_mixtral_moe_forward_and_backward_through_the_experts_registry():
     _compare(ref, ours, ids, atol=5e-5)
     names = [c[0] for c in _fake_ops.CALLS]
     assert names.count("moe_route") == 2 and names.count("moe_combine") == 2 * 2  # fwd un-permute + bwd dX per layer
+    assert names.count("gemm_grouped") == (2 * 4 if inter == 128 else 0)  # per layer: gate|up, down forward + their dgrads
     with torch.no_grad():  # inference path (no autograd bookkeeping) gives the same logits
         torch.testing.assert_close(ours(input_ids=ids).logits, ref(input_ids=ids).logits, atol=5e-5, rtol=1e-4)
 

@@ -102,6 +102,32 @@ def test_gemm_glu_epilogue_is_bit_identical_to_gemm_then_glu(M, I, K, gelu):
     assert torch.equal(g, wg) and torch.equal(u, wu)
 
 
+@pytest.mark.parametrize("counts", [[300, 0, 5, 256, 1027, 64, 9, 130], [512, 512, 512, 512], [0, 0, 77], [4096]])
+@pytest.mark.parametrize("b_mn", [False, True])
+def test_gemm_grouped_matches_per_expert_gemms(counts, b_mn):
+    """b200_gemm_bf16_grouped (row ranges read from device memory, one launch for all experts) vs one b200_gemm_bf16 per
+    expert on the same rows: same tile arithmetic -> bit-identical rows; ragged ranges (not multiples of 8, empty experts,
+    ranges ending inside a 32-row strip), rows beyond the last range untouched.  Forward ([N, K]) and dgrad ([K, N]) layouts."""
+    ops = _ops()
+    E, N, K = len(counts), 320, 192
+    M = sum(counts)
+    off = torch.tensor([0] + list(torch.tensor(counts).cumsum(0)), dtype=torch.int32, device="cuda")
+    a = _randn(M + 40, K, seed=21).cuda()  # 40 extra rows that belong to no expert
+    b = _randn(E, K, N, seed=22, scale=0.1).cuda() if b_mn else _randn(E, N, K, seed=22, scale=0.1).cuda()
+    out = torch.full((M + 40, N), float("nan"), device="cuda", dtype=BF)
+    ops.gemm_grouped(a, b, off, b_mn=b_mn, out=out)
+    lo = 0
+    for e, c in enumerate(counts):
+        if c:
+            want = ops.gemm(a[lo:lo + c], b[e], b_mn=b_mn)
+            if c > 128:  # same CTA-pair kernel family: identical tile arithmetic
+                assert torch.equal(out[lo:lo + c], want), (e, c)
+            else:        # the dispatcher takes the 1-CTA kernel for a single row tile
+                torch.testing.assert_close(out[lo:lo + c].float(), want.float(), atol=1e-2, rtol=1e-2)
+        lo += c
+    assert torch.isnan(out[M:]).all()  # nothing written past the last range
+
+
 def test_rope_table_bit_exact_vs_reference_ops():
     """b200_rope_table vs LlamaRotaryEmbedding.forward's six torch ops (models/llama/modeling_llama.py:113-127) run on the same
     device: fp32 outer product, cat, cos / sin, scale, cast -- bit for bit; and within one bf16 ulp of the CPU oracle."""

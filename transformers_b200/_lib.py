@@ -22,6 +22,7 @@ SIGNATURES = {
     "b200_gemm_bf16": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "b200_gemv_bf16": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "b200_gemm_bf16_2sm": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "b200_gemm_bf16_grouped": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "b200_gemm_glu_bf16": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "b200_gemm_bf16_1sm": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "b200_embedding_fwd": [_p, _p, _p, _i, _i, _i, _f, _i, _p, _p],

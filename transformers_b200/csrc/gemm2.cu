@@ -22,7 +22,8 @@ constexpr int G2_B_BYTES = 128 * G2_BK * 2;   // per CTA: 128 of the 256 B rows
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;  // 32 KB
 constexpr int G2_THREADS = 192;
 constexpr int G2_EPI_BYTES = 4 * 2 * 4096;  // 4 epilogue warps x 2 staging buffers x (32 rows x 128 B), 128B-swizzled for the TMA store
-constexpr int G2_SMEM = G2_STAGES * G2_STAGE_BYTES + G2_EPI_BYTES + 256 + 1024;
+constexpr int G2_MAX_GROUPS = 64;            // experts per grouped launch
+constexpr int G2_SMEM = G2_STAGES * G2_STAGE_BYTES + G2_EPI_BYTES + 256 + 4 * (G2_MAX_GROUPS + 1) + 1024;
 
 struct Gemm2Params {
   __nv_bfloat16* C;
@@ -33,16 +34,26 @@ struct Gemm2Params {
   // SCATTER variant only: row block r (rows_per_owner rows) of the output goes to scatter_maps[r] (tensor maps in global
   // memory, one per destination buffer -- peer-mapped memory of rank r); m_rot rotates the tile order so that the blocks
   // of the other ranks are produced (and travel over NVLink) first, the own block last
-  const CUtensorMap* scatter_maps;
-  int rows_per_owner;
+  union {
+    const CUtensorMap* scatter_maps;
+    const int* offsets;  // GROUPED variant (below); the two variants never combine, the fields share storage
+  };
+  union {
+    int rows_per_owner;
+    int groups;
+  };
   int m_rot;
   // GLU variant only: the weight rows are block-interleaved (256-row groups = 128 gate rows + 128 up rows), so every
   // 256-column output tile holds 128 gate columns and the matching 128 up columns; the epilogue stores them (tmC, the
   // [M, 2I] interleaved gate|up matrix the backward needs) AND act(gate) * up (tmH, [M, I])
   int gelu;
+  // GROUPED variant only (Mixtral experts, integrations/moe.py:377-478): the M rows of A / C are cut into `groups` row
+  // ranges [offsets[g], offsets[g+1]) read from DEVICE memory (the routing kernels wrote them: no host sync), range g is
+  // multiplied by B's g-th [N, K] (or [K, N]) matrix.  Tiles never straddle two ranges: every range starts its own 256-row
+  // tiles, the rows a tile computes beyond its range are not stored.  (`offsets` / `groups`: the unions above.)
 };
 
-constexpr int G2_MODE_PLAIN = 0, G2_MODE_SCATTER = 2, G2_MODE_GLU = 3;
+constexpr int G2_MODE_PLAIN = 0, G2_MODE_SCATTER = 2, G2_MODE_GLU = 3, G2_MODE_GROUPED = 4;
 
 // (A soft lock-step of the persistent clusters at tile boundaries -- to keep co-running tiles walking K together and cut
 // the DRAM re-reads -- was measured in round 2: no step-time gain on the Llama-3-8B shapes, so it is gone;
@@ -59,6 +70,8 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   uint64_t* tfull_bar = empty_bar + G2_STAGES;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;         // [2] (used in the leader CTA only)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  int* g_tile_start = reinterpret_cast<int*>(tmem_slot + 2);  // GROUPED: first tile index of every row range, [groups + 1]
+  constexpr bool GROUPED = MODE == G2_MODE_GROUPED;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -68,10 +81,18 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
   const int num_m = (p.M + G2_BM - 1) / G2_BM;
   const int num_n = (p.N + G2_BN - 1) / G2_BN;
-  const int num_tiles = num_m * num_n;
+  const int num_tiles_dense = num_m * num_n;
   const int num_kb = (p.K + G2_BK - 1) / G2_BK;
 
   if (threadIdx.x == 0) {
+    if constexpr (GROUPED) {
+      int acc = 0;
+      for (int g = 0; g < p.groups; ++g) {
+        g_tile_start[g] = acc;
+        acc += ((p.offsets[g + 1] - p.offsets[g] + G2_BM - 1) / G2_BM) * num_n;
+      }
+      g_tile_start[p.groups] = acc;
+    }
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     prefetch_tmap(&tmC);
@@ -92,6 +113,17 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
   constexpr bool SCATTER = MODE == G2_MODE_SCATTER;
   constexpr bool GLU = MODE == G2_MODE_GLU;
+  const int num_tiles = GROUPED ? g_tile_start[p.groups] : num_tiles_dense;
+  // GROUPED tile -> (row range g, first row of the tile, n tile, end of the range); `g` only moves forward (tiles ascend)
+  auto group_tile = [&](int tile, int& g, int& row0, int& tn, int& row_end) {
+    while (tile >= g_tile_start[g + 1]) ++g;
+    const int lo = p.offsets[g];
+    row_end = p.offsets[g + 1];
+    const int num_m_g = (row_end - lo + G2_BM - 1) / G2_BM;
+    const int local = tile - g_tile_start[g];
+    row0 = lo + (local % num_m_g) * G2_BM;   // m fastest: consecutive tiles share the range's B panel
+    tn = local / num_m_g;
+  };
 
   auto tile_coords = [&](int tile, int& tm, int& tn) {
     const int group_size = p.group_m * num_n;
@@ -111,11 +143,21 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (elect_one()) {  // elect.sync: the compiler keeps UTCHMMA / UTMALDG operands in uniform registers (no per-op ELECT loop)
       int stage = 0;
       uint32_t phase = 0;
+      [[maybe_unused]] int grp = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        int tm, tn;
-        tile_coords(tile, tm, tn);
-        const int m0 = tm * G2_BM + rank * 128;
-        const int n0 = tn * G2_BN + rank * 128;
+        int tm, tn, m0, n0;
+        [[maybe_unused]] int b_k0 = 0;  // GROUPED with an MN-major B: the range's [K, N] matrix starts at row g * K
+        if constexpr (GROUPED) {
+          int row0, row_end;
+          group_tile(tile, grp, row0, tn, row_end);
+          m0 = row0 + rank * 128;
+          n0 = tn * G2_BN + rank * 128 + (B_MN ? 0 : grp * p.N);
+          b_k0 = B_MN ? grp * p.K : 0;
+        } else {
+          tile_coords(tile, tm, tn);
+          m0 = tm * G2_BM + rank * 128;
+          n0 = tn * G2_BN + rank * 128;
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * G2_STAGE_BYTES;
@@ -132,7 +174,8 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             tma_load_2d_2sm(sB, &tmB, leader_full, kb * G2_BK, n0);
           } else {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) tma_load_2d_2sm(sB + j * (64 * G2_BK * 2), &tmB, leader_full, n0 + j * 64, kb * G2_BK);
+            for (int j = 0; j < 2; ++j)
+              tma_load_2d_2sm(sB + j * (64 * G2_BK * 2), &tmB, leader_full, n0 + j * 64, kb * G2_BK + (GROUPED ? b_k0 : 0));
           }
           if (++stage == G2_STAGES) {
             stage = 0;
@@ -177,9 +220,15 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   } else {
     const int q = warp & 3;
     int it = 0;
+    [[maybe_unused]] int grp = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
-      int tm, tn;
-      tile_coords(tile, tm, tn);
+      int tm = 0, tn;
+      [[maybe_unused]] int g_row0 = 0, g_row_end = 0;
+      if constexpr (GROUPED) {
+        group_tile(tile, grp, g_row0, tn, g_row_end);
+      } else {
+        tile_coords(tile, tm, tn);
+      }
       const int buf = it & 1;
       mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
       tc_fence_after();
@@ -250,7 +299,11 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         // writes, no per-thread global stores, M / N tails clipped by the tensor map.  accumulate: the same tile goes out
         // as a TMA reduce-add (C += tile, bf16 adds performed at L2) -- no read-modify-write through the SM
         uint8_t* stage = epi_smem + (warp - 2) * 8192;
-        const int row0 = tm * G2_BM + rank * 128 + q * 32;
+        const int row0 = (GROUPED ? g_row0 : tm * G2_BM) + rank * 128 + q * 32;
+        // GROUPED: a strip that crosses the end of its row range stores its valid rows with plain vector stores (the rows
+        // beyond belong to the next range and are computed by that range's own tile); a strip wholly beyond stores nothing
+        [[maybe_unused]] const bool strip_full = !GROUPED || row0 + 32 <= g_row_end;
+        [[maybe_unused]] const bool lane_valid = !GROUPED || row0 + lane < g_row_end;
 #pragma unroll 1
         for (int c = 0; c < G2_BN / 64; ++c) {
           if (c * 64 >= ncols) break;
@@ -273,7 +326,17 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             o.y = pack_bf16(__uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
             o.z = pack_bf16(__uint_as_float(r[e + 4]), __uint_as_float(r[e + 5]));
             o.w = pack_bf16(__uint_as_float(r[e + 6]), __uint_as_float(r[e + 7]));
+            if constexpr (GROUPED) {
+              if (!strip_full) {
+                if (lane_valid)
+                  *reinterpret_cast<uint4*>(p.C + static_cast<size_t>(row0 + lane) * p.ldc + tn * G2_BN + c * 64 + v * 8) = o;
+                continue;
+              }
+            }
             *reinterpret_cast<uint4*>(srow + ((v ^ (lane & 7)) << 4)) = o;  // 128B swizzle: 16-byte chunk index ^ (row % 8)
+          }
+          if constexpr (GROUPED) {
+            if (!strip_full) continue;  // warp-uniform
           }
           fence_proxy_async();
           __syncwarp();
@@ -308,14 +371,14 @@ gemm_bf16_tcgen05_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
 template <int A_MN, int B_MN, int MODE>
 static int launch_gemm2_v(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmH,
-                          Gemm2Params p, cudaStream_t stream) {
+                          Gemm2Params p, cudaStream_t stream, int tiles_override = 0) {
   auto kern = gemm_bf16_tcgen05_2sm<A_MN, B_MN, MODE>;
   static bool attr_set = false;
   if (!attr_set) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
     attr_set = true;
   }
-  const int num_tiles = ((p.M + G2_BM - 1) / G2_BM) * ((p.N + G2_BN - 1) / G2_BN);
+  const int num_tiles = tiles_override > 0 ? tiles_override : ((p.M + G2_BM - 1) / G2_BM) * ((p.N + G2_BN - 1) / G2_BN);
   int sms = num_sms();
   if (sms <= 0) {
     set_last_error("no CUDA device");
@@ -433,6 +496,52 @@ extern "C" int b200_gemm_glu_bf16(const void* A, const void* W, void* gu, void* 
   p.m_rot = 0;
   p.gelu = gelu & 1;
   return launch_gemm2_v<0, 0, G2_MODE_GLU>(tmA, tmB, tmC, tmH, p, stream);
+}
+
+// Grouped GEMM for mixture-of-experts blocks (MixtralExperts.forward models/mixtral/modeling_mixtral.py:69-93 /
+// grouped_mm_experts_forward integrations/moe.py:377-478): rows [offsets[g], offsets[g+1]) of A [M_total, K] -- the tokens
+// routed to expert g, sorted by expert -- are multiplied by expert g's matrix, B + g * N * K ([N, K] K-major; or [K, N] when
+// b_mn, the dgrad layout) into the same rows of C [M_total, N].  `offsets` is an int32[groups + 1] array in DEVICE memory
+// (written by b200_moe_route): no host synchronisation, one launch for all experts.  N % 64 == 0; b_mn needs K % 64 == 0.
+extern "C" int b200_gemm_bf16_grouped(const void* A, const void* B, void* C, const int* offsets, int groups, int M_total, int N,
+                                      int K, int lda, int ldb, int ldc, int b_mn, cudaStream_t stream) {
+  using namespace b200;
+  B200_REQUIRE(groups >= 1 && groups <= G2_MAX_GROUPS, "gemm_grouped: %d groups (1..%d)", groups, G2_MAX_GROUPS);
+  B200_REQUIRE(M_total >= 0 && N > 0 && K > 0 && N % 64 == 0 && (!b_mn || K % 64 == 0),
+               "gemm_grouped: needs N %% 64 == 0 (and K %% 64 == 0 for the dgrad layout), got M=%d N=%d K=%d", M_total, N, K);
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0 && ldc % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && offsets != nullptr,
+               "gemm_grouped: C must be 16B aligned, leading dimensions multiples of 8, offsets non-null");
+  if (M_total == 0) return B200_OK;
+  CUtensorMap tmA, tmB, tmC;
+  int rc;
+  if ((rc = make_tmap_2d_bf16(&tmA, A, M_total, K, lda, G2_BK, 128))) return rc;
+  if (!b_mn)
+    rc = make_tmap_2d_bf16(&tmB, B, static_cast<uint64_t>(groups) * N, K, ldb, G2_BK, 128);
+  else
+    rc = make_tmap_2d_bf16(&tmB, B, static_cast<uint64_t>(groups) * K, N, ldb, 64, G2_BK);
+  if (rc) return rc;
+  if ((rc = make_tmap_2d_bf16(&tmC, C, M_total, N, ldc, 64, 32))) return rc;
+  Gemm2Params p;
+  p.C = reinterpret_cast<__nv_bfloat16*>(C);
+  p.M = M_total;
+  p.N = N;
+  p.K = K;
+  p.ldc = ldc;
+  p.accumulate = 0;
+  p.group_m = 8;
+  const uint32_t k_lbo = 16, k_sbo = 1024, mn_lbo = 64 * G2_BK * 2, mn_sbo = 1024;
+  p.a_lbo = k_lbo;
+  p.a_sbo = k_sbo;
+  p.b_lbo = b_mn ? mn_lbo : k_lbo;
+  p.b_sbo = b_mn ? mn_sbo : k_sbo;
+  p.m_rot = 0;
+  p.gelu = 0;
+  p.offsets = offsets;
+  p.groups = groups;
+  // the tile count lives on the device; size the persistent grid for the worst case (every range adds one partial m tile)
+  const int max_tiles = ((M_total + G2_BM - 1) / G2_BM + groups) * ((N + G2_BN - 1) / G2_BN);
+  return b_mn ? launch_gemm2_v<0, 1, G2_MODE_GROUPED>(tmA, tmB, tmC, tmC, p, stream, max_tiles)
+              : launch_gemm2_v<0, 0, G2_MODE_GROUPED>(tmA, tmB, tmC, tmC, p, stream, max_tiles);
 }
 
 // GEMM whose epilogue is the first half of a reduce-scatter: D = A B^T as b200_gemm_bf16, but row block r of the output

@@ -689,30 +689,39 @@ class MoEExpertsFn(torch.autograd.Function):
         k = top_k_index.shape[1]
         E = gate_up.shape[0]
         offsets, slot, tok = ops.moe_route(top_k_index, E)
-        off = offsets.tolist()  # one host sync per MoE block: expert row ranges are launch parameters of the GEMMs
         xs = ops.moe_gather(x, tok)
         n = xs.shape[0]
-        gu = torch.empty(n, gate_up.shape[1], device=x.device, dtype=x.dtype)
-        ys = torch.empty(n, H, device=x.device, dtype=x.dtype)
-        for e in range(E):
-            lo, hi = off[e], off[e + 1]
-            if hi > lo:
-                ops.gemm(xs[lo:hi], gate_up[e], out=gu[lo:hi])
-        act = ops.glu_fwd(gu, gelu)
-        for e in range(E):
-            lo, hi = off[e], off[e + 1]
-            if hi > lo:
-                ops.gemm(act[lo:hi], down[e], out=ys[lo:hi])
+        grouped = ops.grouped_ok(gate_up, down)
+        off = None
+        if grouped:  # one grouped GEMM per projection, expert row ranges read from the device (no host sync in the forward)
+            gu = ops.gemm_grouped(xs, gate_up, offsets)
+            act = ops.glu_fwd(gu, gelu)
+            ys = ops.gemm_grouped(act, down, offsets)
+        else:
+            off = offsets.tolist()  # per-expert launches: their row ranges are host-side launch parameters
+            gu = torch.empty(n, gate_up.shape[1], device=x.device, dtype=x.dtype)
+            ys = torch.empty(n, H, device=x.device, dtype=x.dtype)
+            for e in range(E):
+                lo, hi = off[e], off[e + 1]
+                if hi > lo:
+                    ops.gemm(xs[lo:hi], gate_up[e], out=gu[lo:hi])
+            act = ops.glu_fwd(gu, gelu)
+            for e in range(E):
+                lo, hi = off[e], off[e + 1]
+                if hi > lo:
+                    ops.gemm(act[lo:hi], down[e], out=ys[lo:hi])
         out = ops.moe_combine(ys, slot, top_k_weights, T, k)
-        ctx.save_for_backward(xs, gu, act, ys, slot, tok, top_k_weights, gate_up, down)
-        ctx.cfg = (off, gelu, T, k)
+        ctx.save_for_backward(xs, gu, act, ys, slot, tok, top_k_weights, gate_up, down, offsets)
+        ctx.cfg = (off, gelu, T, k, grouped)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        xs, gu, act, ys, slot, tok, weights, gate_up, down = ctx.saved_tensors
-        off, gelu, T, k = ctx.cfg
+        xs, gu, act, ys, slot, tok, weights, gate_up, down, offsets = ctx.saved_tensors
+        off, gelu, T, k, grouped = ctx.cfg
         E = gate_up.shape[0]
+        if off is None:  # the weight gradients are per-expert GEMMs over the expert's rows (K-grouped): host-side ranges
+            off = offsets.tolist()
         dout = dout.contiguous()
         g = ops.moe_gather(dout, tok)  # dOut of the token behind every sorted slot
         slot_l = slot.long()
@@ -723,21 +732,23 @@ class MoEExpertsFn(torch.autograd.Function):
         w_sorted = torch.empty(slot.numel(), device=g.device, dtype=torch.float32)
         w_sorted[slot_l] = weights.reshape(-1).float()
         dys = (g.float() * w_sorted[:, None]).to(g.dtype)
-        dact = torch.empty_like(act)
+        dact = ops.gemm_grouped(dys, down, offsets, b_mn=True) if grouped else torch.empty_like(act)
         d_down = torch.zeros_like(down) if ctx.needs_input_grad[4] else None
         for e in range(E):
             lo, hi = off[e], off[e + 1]
             if hi > lo:
-                ops.gemm(dys[lo:hi], down[e], b_mn=True, out=dact[lo:hi])
+                if not grouped:
+                    ops.gemm(dys[lo:hi], down[e], b_mn=True, out=dact[lo:hi])
                 if d_down is not None:
                     ops.gemm(dys[lo:hi], act[lo:hi], a_mn=True, b_mn=True, out=d_down[e])
         dgu = ops.glu_bwd(dact, gu, gelu)
-        dxs = torch.empty_like(xs)
+        dxs = ops.gemm_grouped(dgu, gate_up, offsets, b_mn=True) if grouped else torch.empty_like(xs)
         d_gate_up = torch.zeros_like(gate_up) if ctx.needs_input_grad[3] else None
         for e in range(E):
             lo, hi = off[e], off[e + 1]
             if hi > lo:
-                ops.gemm(dgu[lo:hi], gate_up[e], b_mn=True, out=dxs[lo:hi])
+                if not grouped:
+                    ops.gemm(dgu[lo:hi], gate_up[e], b_mn=True, out=dxs[lo:hi])
                 if d_gate_up is not None:
                     ops.gemm(dgu[lo:hi], xs[lo:hi], a_mn=True, b_mn=True, out=d_gate_up[e])
         dx = None

@@ -118,6 +118,34 @@ def gemm_glu(a: torch.Tensor, w_ilv: torch.Tensor, gelu: bool = False, gu_out: t
     return gu, h
 
 
+def gemm_grouped(a: torch.Tensor, b: torch.Tensor, offsets: torch.Tensor, *, b_mn: bool = False,
+                 out: torch.Tensor | None = None) -> torch.Tensor:
+    """Rows [offsets[g], offsets[g+1]) of a [M, K] times expert g's matrix b[g] ([N, K], or [K, N] when ``b_mn``) -> the same
+    rows of out [M, N]; ``offsets`` int32 [G + 1] on the device (no host sync, one launch for all experts)."""
+    lib = _lib_ready()
+    _chk_bf16(a, b, out)
+    G = b.shape[0]
+    M, K = a.shape
+    N = b.shape[2] if b_mn else b.shape[1]
+    if b.dim() != 3 or not b.is_contiguous() or a.stride(1) != 1 or (b.shape[1] if b_mn else b.shape[2]) != K:
+        raise B200Error("gemm_grouped: b must be a contiguous [G, N, K] (or [G, K, N]) tensor matching a's contraction")
+    if offsets.dtype != torch.int32 or offsets.numel() != G + 1 or not offsets.is_cuda:
+        raise B200Error("gemm_grouped: offsets must be a device int32 tensor with G + 1 entries")
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=BF16)
+    if out.shape != (M, N) or out.stride(1) != 1:
+        raise B200Error("gemm_grouped: bad output tensor")
+    check(lib.b200_gemm_bf16_grouped(a.data_ptr(), b.data_ptr(), out.data_ptr(), offsets.data_ptr(), G, M, N, K, a.stride(0),
+                                     b.stride(1), out.stride(0), int(b_mn), _stream()), "b200_gemm_bf16_grouped")
+    return out
+
+
+def grouped_ok(gate_up: torch.Tensor, down: torch.Tensor) -> bool:
+    """Expert stacks the grouped kernel takes (<= 64 experts, widths in whole 64-column chunks)."""
+    E, I2, H = gate_up.shape
+    return E <= 64 and I2 % 64 == 0 and H % 64 == 0 and down.shape[2] % 64 == 0 and gate_up.is_contiguous() and down.is_contiguous()
+
+
 def glu_fusable(M: int, I: int) -> bool:
     """Shapes the GLU-epilogue GEMM takes (CTA-pair kernel: more than one 128-row tile; whole 128-column blocks)."""
     return M > 128 and I % GLU_BLOCK == 0
@@ -375,18 +403,24 @@ def moe_experts_forward(x: torch.Tensor, top_k_index: torch.Tensor, top_k_weight
     xs = torch.empty(n, H, device=dev, dtype=BF16)
     x = x.contiguous()
     check(lib.b200_moe_gather(x.data_ptr(), tok.data_ptr(), xs.data_ptr(), n, H, _stream()), "b200_moe_gather")
-    off = offsets.tolist()  # one host sync per MoE block: the expert GEMM shapes are host-side launch parameters
-    gu = torch.empty(n, 2 * I, device=dev, dtype=BF16)
-    ys = torch.empty(n, H, device=dev, dtype=BF16)
-    for e in range(E):
-        lo, hi = off[e], off[e + 1]
-        if hi > lo:
-            gemm(xs[lo:hi], gate_up[e], out=gu[lo:hi])
-    act = glu_fwd(gu, gelu)
-    for e in range(E):
-        lo, hi = off[e], off[e + 1]
-        if hi > lo:
-            gemm(act[lo:hi], down[e], out=ys[lo:hi])
+    if grouped_ok(gate_up, down):
+        # ONE grouped GEMM per projection: the expert row ranges stay on the device (no host sync, no per-expert launches)
+        gu = gemm_grouped(xs, gate_up, offsets)
+        act = glu_fwd(gu, gelu)
+        ys = gemm_grouped(act, down, offsets)
+    else:
+        off = offsets.tolist()  # odd widths: per-expert launches, their row ranges are host-side launch parameters
+        gu = torch.empty(n, 2 * I, device=dev, dtype=BF16)
+        ys = torch.empty(n, H, device=dev, dtype=BF16)
+        for e in range(E):
+            lo, hi = off[e], off[e + 1]
+            if hi > lo:
+                gemm(xs[lo:hi], gate_up[e], out=gu[lo:hi])
+        act = glu_fwd(gu, gelu)
+        for e in range(E):
+            lo, hi = off[e], off[e + 1]
+            if hi > lo:
+                gemm(act[lo:hi], down[e], out=ys[lo:hi])
     out = torch.empty(T, H, device=dev, dtype=BF16)
     check(lib.b200_moe_combine(ys.data_ptr(), slot.data_ptr(), w.data_ptr(), out.data_ptr(), T, k, H, _stream()), "b200_moe_combine")
     return out
