@@ -37,11 +37,12 @@ def workload_name(world: int, batch: int, seq: int) -> str:
 
 
 def ncu_gemm_traffic():
-    """DRAM bytes (read + write) per launch of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/r01_ncu_summary_final.csv: gate|up fwd, dgrad and wgrad GEMMs at the Llama-3-8B shapes); None if absent."""
+    """DRAM bytes (read + write) per launch of the dominant kernel from the committed `ncu --set full` capture of round 2
+    (profiles/r02_ncu_summary.csv: the gate|up-shaped fwd, dgrad and wgrad GEMMs at the Llama-3-8B shapes, incl. the
+    GLU-epilogue and reduce-add variants); None if absent."""
     import csv
 
-    path = os.path.join(ROOT, "profiles", "r01_ncu_summary_final.csv")
+    path = os.path.join(ROOT, "profiles", "r02_ncu_summary.csv")
     try:
         rows = list(csv.reader(open(path)))
         hdr, units = rows[0], rows[1]
@@ -540,7 +541,7 @@ def run_b200(args):
                          "frac": (gemm_fl / (gemm_ms * 1e-3) / 1e12 / peak_tf) if gemm_ms else None, "peak_source": peak_src,
                          "traffic": ncu_gemm_traffic(),
                          "traffic_note": "mean DRAM read+write bytes per launch over the 16384x28672x4096 fwd / dgrad / wgrad GEMMs of "
-                                         "profiles/r01_ncu_summary_final.csv (algorithmic: 1.31 GB each)",
+                                         "profiles/r02_ncu_summary.csv (algorithmic: 1.31 GB each; 1.78 GB for the GLU-epilogue variant)",
                          "share_of_step": gemm_ms / ours_ms if ours_ms else None,
                          "whole_step_frac": per_gpu_tf / peak_tf},
             "kernels_ms": {k: {"ms": round(v[0], 3), "launches": v[1]} for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])},
