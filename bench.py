@@ -432,7 +432,18 @@ def run_b200(args):
             args.sequence_parallel = 1  # the peer transport uses one row block per rank
             from transformers_b200.symm import PeerWorkspace
 
-            peer_ws = PeerWorkspace(dist.group.WORLD, scatter_epilogue=args.tp_transport == "peer-scatter")
+            try:  # symmetric (peer-mapped) allocations are a collective: reserve them now, for the largest buffer of the step
+                peer_ws = PeerWorkspace(dist.group.WORLD, scatter_epilogue=args.tp_transport == "peer-scatter")
+                peer_ws.reserve(args.batch * args.seq * LLAMA3_8B["hidden_size"])
+                ok = torch.ones(1, device="cuda")
+            except Exception as exc:  # e.g. no peer access between the GPUs of this box: say so and use NCCL for the same plan
+                print(f"[bench] rank {rank}: peer-memory workspace unavailable ({type(exc).__name__}: {exc})", file=sys.stderr)
+                peer_ws, ok = None, torch.zeros(1, device="cuda")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() == 0:
+                peer_ws = None
+                args.tp_transport = "nccl"
+                args.sequence_parallel = max(args.sequence_parallel, 2)
         tensor_parallelize(model, dist.group.WORLD, sequence_parallel=args.sequence_parallel > 0,
                            chunks=max(args.sequence_parallel, 1), vocab_parallel_loss=bool(args.vocab_parallel_loss),
                            peer_workspace=peer_ws)

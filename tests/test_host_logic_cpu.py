@@ -129,3 +129,36 @@ def test_c_abi_validates_new_entry_points_without_a_gpu():
     assert lib.b200_grad_scale(None, None, -1, None, None) == -22
     assert lib.b200_ce_bwd_sharded(None, None, None, None, None, 4, 64, 60, 64, None) == -22  # ld % 8
     assert lib.b200_optim_chunk_elems() == 32768
+
+
+def test_deferred_embedding_range_flag():
+    """Out-of-range token ids are reported at the next call, once the kernel that raised the flag has finished, without a
+    host sync on the hot path (the flag was written but never read)."""
+    from transformers_b200 import B200Error
+    from transformers_b200.ops import _DeferredFlag
+
+    class Ev:
+        def __init__(self, done):
+            self.done = done
+
+        def query(self):
+            return self.done
+
+        def synchronize(self):
+            self.done = True
+
+    d = _DeferredFlag()
+    busy = Ev(False)
+    d.push(torch.ones(1, dtype=torch.int32), busy)   # bad ids, kernel still running: nothing to read yet
+    d.poll()
+    assert len(d.pending) == 1
+    busy.done = True
+    with pytest.raises(B200Error):
+        d.poll()
+    assert d.pending == []
+    d.push(torch.zeros(1, dtype=torch.int32), Ev(True))
+    d.poll()
+    assert d.pending == []
+    d.push(torch.ones(1, dtype=torch.int32), Ev(False))
+    with pytest.raises(B200Error):
+        d.poll(force=True)

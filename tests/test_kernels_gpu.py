@@ -128,6 +128,25 @@ def test_gemm_grouped_matches_per_expert_gemms(counts, b_mn):
     assert torch.isnan(out[M:]).all()  # nothing written past the last range
 
 
+def test_embedding_out_of_range_ids_are_reported():
+    """Token ids outside the table raise (the reference's F.embedding device-asserts): not at the offending call -- that would
+    cost a host sync per forward -- but at the next embedding call / embedding_check_now()."""
+    ops = _ops()
+    from transformers_b200 import B200Error
+
+    ops.embedding_check_now()
+    V, H = 100, 64
+    w = _randn(V, H, seed=8).cuda()
+    ok = ops.embedding_fwd(torch.tensor([[1, 2, 99]]).cuda(), w)
+    assert torch.equal(ok[0, 2], w[99])
+    ops.embedding_check_now()
+    ops.embedding_fwd(torch.tensor([[3, V + 5, 7]]).cuda(), w)  # bad id: flagged on the device, reported later
+    torch.cuda.synchronize()
+    with pytest.raises(B200Error):
+        ops.embedding_fwd(torch.tensor([[1]]).cuda(), w)
+    ops.embedding_check_now()  # the report cleared the pending flags
+
+
 def test_rope_table_bit_exact_vs_reference_ops():
     """b200_rope_table vs LlamaRotaryEmbedding.forward's six torch ops (models/llama/modeling_llama.py:113-127) run on the same
     device: fp32 outer product, cat, cos / sin, scale, cast -- bit for bit; and within one bf16 ulp of the CPU oracle."""

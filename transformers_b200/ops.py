@@ -152,9 +152,47 @@ def glu_fusable(M: int, I: int) -> bool:
 
 
 # ------------------------------------------------------------------------------------------------------ embedding
+class _DeferredFlag:
+    """Out-of-range token ids: the gather kernel raises a device flag instead of asserting (the reference's F.embedding
+    device-asserts).  Reading the flag right away would put a host sync on every forward, so it is read at the NEXT call --
+    by then the kernel that wrote it has long finished (``event.query()``; if it has not, the check moves on to the call
+    after) -- and raises there.  The flag travels to PINNED host memory with an asynchronous copy right behind the kernel, so
+    reading it never synchronises the stream (a ``.item()`` on the device flag would wait for everything queued behind it).
+    ``poll(force=True)`` waits for the copies (tests, end of a step)."""
+
+    def __init__(self):
+        self.pending = []  # (flag tensor, event or None)
+
+    def push(self, flag, event=None):
+        self.pending.append((flag, event))
+
+    def poll(self, force: bool = False):
+        keep = []
+        for flag, event in self.pending:
+            if force and event is not None:
+                event.synchronize()
+            if force or event is None or event.query():
+                if int(flag[0]) != 0:
+                    self.pending = []
+                    raise B200Error("embedding: input_ids contain values outside [0, num_embeddings) "
+                                    "(detected at the call after the offending forward)")
+            else:
+                keep.append((flag, event))
+        self.pending = keep
+
+
+_EMBED_FLAGS = _DeferredFlag()
+
+
+def embedding_check_now() -> None:
+    """Synchronously raise if any earlier embedding gather saw an out-of-range token id."""
+    _EMBED_FLAGS.poll(force=True)
+
+
 def embedding_fwd(ids: torch.Tensor, weight: torch.Tensor, scale: float | None = None) -> torch.Tensor:
     lib = _lib_ready()
     _chk_bf16(weight)
+    _EMBED_FLAGS.poll()
     ids_c = ids.contiguous().view(-1)
     if ids_c.dtype != torch.int64:
         ids_c = ids_c.to(torch.int64)
@@ -165,6 +203,11 @@ def embedding_fwd(ids: torch.Tensor, weight: torch.Tensor, scale: float | None =
     check(lib.b200_embedding_fwd(ids_c.data_ptr(), w.data_ptr(), out.data_ptr(), T, H, V,
                                  float(scale) if scale is not None else 1.0, int(scale is not None), err.data_ptr(), _stream()),
           "b200_embedding_fwd")
+    host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+    host.copy_(err, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    _EMBED_FLAGS.push(host, ev)
     return out
 
 
