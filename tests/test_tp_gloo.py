@@ -119,9 +119,8 @@ def _worker(rank, world, port, q, mode, sp, S=12, vp=False, peer=False, inter=17
 
 @pytest.mark.timeout(300)
 @pytest.mark.parametrize("mode,sp,S,vp,peer,inter", [("stock", False, 12, False, False, 176), ("stock", True, 12, False, False, 176),
-                                                     ("kernel-path", False, 12, False, False, 176), ("kernel-path", True, 12, True, False, 176),
+                                                     ("kernel-path", True, 12, True, False, 176),
                                                      ("kernel-path", False, 256, True, False, 176), ("kernel-path", True, 12, False, True, 176),
-                                                     ("kernel-path", True, 256, False, "scatter", 176),
                                                      ("kernel-path", False, 96, False, False, 256), ("kernel-path", True, 384, True, False, 512),
                                                      ("kernel-path", True, 256, True, "scatter", 256)])
 def test_tp2_matches_single_process_gloo(mode, sp, S, vp, peer, inter):
