@@ -11,6 +11,7 @@
 #include "elementwise.cu"
 #include "kvcache.cu"
 #include "moe.cu"
+#include "rope_table.cu"
 
 using namespace b200;
 
@@ -163,6 +164,13 @@ extern "C" int emu_rope(void* qkv, const void* c, const void* s, int B, int S, i
   auto *cp = reinterpret_cast<const bf*>(c), *sp = reinterpret_cast<const bf*>(s);
   if (bwd) emu::launch(dim3(T), dim3(threads), [&] { rope_kernel<true>(q, cp, sp, T, S, n_rot, D, row_stride, cbs); });
   else emu::launch(dim3(T), dim3(threads), [&] { rope_kernel<false>(q, cp, sp, T, S, n_rot, D, row_stride, cbs); });
+  return 0;
+}
+extern "C" int emu_rope_table(const float* inv_freq, const int64_t* pos, void* c, void* s, int rows, int D, float scaling) {
+  const int half = D / 2;
+  emu::launch(dim3(cdiv(rows * half, 256)), dim3(256), [&] {
+    rope_table_kernel(inv_freq, pos, reinterpret_cast<bf*>(c), reinterpret_cast<bf*>(s), rows, half, scaling);
+  });
   return 0;
 }
 extern "C" int emu_glu_fwd(const void* g, const void* u, void* out, int T, int I, int ld_gu, int ld_out, int gelu) {

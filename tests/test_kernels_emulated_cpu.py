@@ -190,6 +190,7 @@ def emu2(emu):
     emu.emu_rmsnorm_fwd.argtypes = [p, p, p, p, p, p, i32, i32, f32, i32]
     emu.emu_rmsnorm_bwd.argtypes = [p, p, p, p, p, p, p, i32, i32, i32, i32]
     emu.emu_rope.argtypes = [p, p, p, i32, i32, i32, i32, i32, i32, i32]
+    emu.emu_rope_table.argtypes = [p, p, p, p, i32, i32, f32]
     emu.emu_glu_fwd.argtypes = [p, p, p, i32, i32, i32, i32, i32]
     emu.emu_glu_bwd.argtypes = [p, p, p, p, p, i32, i32, i32, i32, i32, i32]
     emu.emu_add.argtypes = [p, p, p, i64]
@@ -414,3 +415,23 @@ def test_adamw_master_weights_kernel_emulated(emu):
         assert torch.equal(pb, master.to(BF))
     assert (master - master.to(BF).float()).abs().max() > 0  # the master really carries sub-ulp information
     torch.testing.assert_close(master, ref_p, atol=2e-6, rtol=1e-4)  # moments are bf16 here, the oracle's are fp32
+
+
+@pytest.mark.timeout(300)
+def test_rope_table_kernel_emulated(emu2):
+    """rope_table.cu (the cos / sin tables of LlamaRotaryEmbedding.forward, models/llama/modeling_llama.py:113-127) executed
+    on the host against the oracle: same products, same cat(freqs, freqs) layout, one bf16 ulp at most (host cosf vs torch)."""
+    from oracle import decoder_oracle as O
+
+    cfg = O.DecoderConfig(vocab_size=8, hidden_size=64, intermediate_size=64, num_hidden_layers=1, num_attention_heads=1,
+                          num_key_value_heads=1, head_dim=64, rope_theta=500000.0)
+    inv = O.rope_inv_freq(cfg).contiguous()
+    pos = torch.stack([torch.arange(37), torch.arange(37) + 5000]).contiguous()
+    for scaling in (1.0, 0.75):
+        cos = torch.empty(2, 37, 64, dtype=BF)
+        sin = torch.empty(2, 37, 64, dtype=BF)
+        emu2.emu_rope_table(inv.data_ptr(), pos.data_ptr(), cos.data_ptr(), sin.data_ptr(), 2 * 37, 64, scaling)
+        want_cos, want_sin = O.rope_tables(inv, pos, BF, attention_scaling=scaling)
+        assert torch.equal(cos[..., :32], cos[..., 32:]) and torch.equal(sin[..., :32], sin[..., 32:])
+        assert (cos.float() - want_cos.float()).abs().max() <= 2 ** -7 and (sin.float() - want_sin.float()).abs().max() <= 2 ** -7
+        assert (cos != want_cos).float().mean() < 0.01 and (sin != want_sin).float().mean() < 0.01

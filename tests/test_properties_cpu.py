@@ -131,3 +131,62 @@ def test_scatter_tile_order_visits_every_tile_once_and_own_block_last(world, blo
         first_own = owners_in_order.index(rank)
         assert all(o == rank for o in owners_in_order[first_own:]) or group_m > 1  # strict "own block last" holds for group_m == 1
         assert owners_in_order[-1] == rank or group_m > 1
+
+
+@settings(max_examples=60, deadline=None)
+@given(rows=st.lists(st.lists(st.integers(1, 9), min_size=1, max_size=6), min_size=1, max_size=3))
+def test_packed_sequence_ranges_partition_every_row(rows):
+    """modules.SegmentIds.ranges(): from the sequence indices the reference derives for a packed batch
+    (find_packed_sequence_indices, masking_utils.py:728-757) to the (start, end) token ranges the attention Functions launch
+    on: every row is partitioned exactly at the places where the index changes."""
+    from transformers_b200.modules import SegmentIds
+
+    S = max(sum(r) for r in rows)
+    lens = [r + ([S - sum(r)] if sum(r) < S else []) for r in rows]
+    pos = torch.stack([torch.cat([torch.arange(n) for n in r]) for r in lens])
+    first = pos[:, :1] - 1
+    ids = (torch.diff(pos, prepend=first, dim=-1) != 1).cumsum(-1)  # the reference's formula
+    got = SegmentIds(ids).ranges()
+    assert len(got) == len(lens)
+    for r, segs in zip(lens, got):
+        ends = torch.tensor(r).cumsum(0).tolist()
+        assert segs == list(zip([0] + ends[:-1], ends))
+
+
+@settings(max_examples=40, deadline=None)
+@given(blocks=st.integers(1, 6), K=st.integers(1, 5))
+def test_gate_up_interleave_round_trips(blocks, K):
+    """ops.interleave_gate_up / deinterleave_gate_up: 128-row blocks alternate gate / up; the inverse returns the inputs; row j
+    of gate sits at (j // 128) * 256 + j % 128, the matching up row 128 further."""
+    from transformers_b200 import ops
+
+    I = 128 * blocks
+    wg = torch.arange(I * K, dtype=torch.float32).view(I, K)
+    wu = -wg - 1
+    ilv = ops.interleave_gate_up(wg, wu)
+    assert ilv.shape == (2 * I, K)
+    j = torch.arange(I)
+    at = (j // 128) * 256 + j % 128
+    assert torch.equal(ilv[at], wg) and torch.equal(ilv[at + 128], wu)
+    g, u = ops.deinterleave_gate_up(ilv)
+    assert torch.equal(g, wg) and torch.equal(u, wu)
+
+
+@settings(max_examples=40, deadline=None)
+@given(cu=st.lists(st.integers(1, 50), min_size=1, max_size=8))
+def test_cu_seq_lens_become_ranges_or_are_refused(cu):
+    """SegmentIds.from_cu_seqlens: cumulative lengths of a flattened batch (modeling_flash_attention_utils.py:570-590) -> one row
+    of ranges; lists that do not partition the batch raise."""
+    import pytest
+
+    from transformers_b200 import B200Error
+    from transformers_b200.modules import SegmentIds
+
+    ends = torch.tensor(cu).cumsum(0).tolist()
+    total = ends[-1]
+    seg = SegmentIds.from_cu_seqlens(torch.tensor([0] + ends, dtype=torch.int32), total)
+    assert seg.ranges() == [list(zip([0] + ends[:-1], ends))]
+    with pytest.raises(B200Error):
+        SegmentIds.from_cu_seqlens([0] + ends, total + 1)
+    with pytest.raises(B200Error):
+        SegmentIds.from_cu_seqlens([1] + ends, total)
