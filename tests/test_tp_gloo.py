@@ -41,7 +41,7 @@ def _worker(rank, world, port, q, mode, sp, S=12, vp=False, peer=False, inter=17
 
         transformers_b200.enable()
         cfg = tf.LlamaConfig(vocab_size=160, hidden_size=64, intermediate_size=inter, num_hidden_layers=2, num_attention_heads=4,
-                             num_key_value_heads=2, head_dim=16, max_position_embeddings=512,
+                             num_key_value_heads=2 if world <= 2 else 4, head_dim=16, max_position_embeddings=1024,
                              rope_parameters={"rope_type": "default", "rope_theta": 10000.0})
         tf.set_seed(0)
         model = tf.LlamaForCausalLM._from_config(cfg, attn_implementation="eager", dtype=torch.float32)
@@ -71,7 +71,7 @@ def _worker(rank, world, port, q, mode, sp, S=12, vp=False, peer=False, inter=17
             model.set_attn_implementation("b200")
             model.loss_function = transformers_b200.integration.b200_causal_lm_loss
         att = model.model.layers[0].self_attn
-        assert att.q_proj.weight.shape == (4 * 16 // world, 64) and att.k_proj.weight.shape == (2 * 16 // world, 64)
+        assert att.q_proj.weight.shape == (4 * 16 // world, 64) and att.k_proj.weight.shape == (cfg.num_key_value_heads * 16 // world, 64)
         assert att.o_proj.weight.shape == (64, 4 * 16 // world)
         assert model.model.layers[0].mlp.down_proj.weight.shape == (64, inter // world)
         assert model.lm_head.weight.shape == (160 // world, 64)
@@ -124,7 +124,17 @@ def _worker(rank, world, port, q, mode, sp, S=12, vp=False, peer=False, inter=17
                                                      ("kernel-path", False, 96, False, False, 256), ("kernel-path", True, 384, True, False, 512),
                                                      ("kernel-path", True, 256, True, "scatter", 256)])
 def test_tp2_matches_single_process_gloo(mode, sp, S, vp, peer, inter):
-    world = 2
+    _run(2, mode, sp, S, vp, peer, inter)
+
+
+@pytest.mark.timeout(300)
+def test_tp4_peer_scatter_matches_single_process_gloo():
+    """Four ranks (the N = 4 point of the scaling run): sequence parallelism + vocabulary-parallel loss + the peer-memory
+    transport with the GEMM scatter epilogue and the GLU-epilogue GEMM on each rank's column shard."""
+    _run(4, "kernel-path", True, 512, True, "scatter", 512)
+
+
+def _run(world, mode, sp, S, vp, peer, inter):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
