@@ -157,6 +157,15 @@ def repeat_kv(hidden_states: torch.Tensor, n_rep: int) -> torch.Tensor:
     return hidden_states.reshape(batch, num_key_value_heads * n_rep, slen, head_dim)
 
 
+def packed_sequence_ids(position_ids: torch.Tensor) -> torch.Tensor | None:
+    """find_packed_sequence_indices masking_utils.py:728-757: the index of the sequence every token of a padding-free packed
+    batch belongs to (a new sequence starts wherever consecutive position ids do not differ by one); None when no row holds
+    more than one sequence."""
+    first = position_ids[:, :1] - 1
+    ids = (torch.diff(position_ids, prepend=first, dim=-1) != 1).cumsum(-1)
+    return None if bool((ids[:, -1] == 0).all()) else ids
+
+
 def eager_mask(
     batch: int,
     q_len: int,
@@ -165,10 +174,12 @@ def eager_mask(
     q_offset: int = 0,
     sliding_window: int | None = None,
     padding_mask: torch.Tensor | None = None,
+    sequence_ids: torch.Tensor | None = None,
 ) -> torch.Tensor:
     """The additive 4-D mask the eager backend receives: 0 where attended, finfo(dtype).min elsewhere.
     causal_mask_function masking_utils.py:76-80 (kv_idx <= q_idx), sliding_window_overlay :92-101
-    (kv_idx > q_idx - sliding_window), padding :104-115, eager_mask :538-604 (min-value fill :599-603)."""
+    (kv_idx > q_idx - sliding_window), padding :104-115, packed_sequence_mask_function :182-190 (q and kv in the same sequence,
+    and-ed in by create_causal_mask :973-974), eager_mask :538-604 (min-value fill :599-603)."""
     q_idx = torch.arange(q_len)[:, None] + q_offset
     kv_idx = torch.arange(kv_len)[None, :]
     allowed = kv_idx <= q_idx
@@ -177,6 +188,8 @@ def eager_mask(
     allowed = allowed[None, None].expand(batch, 1, q_len, kv_len)
     if padding_mask is not None:
         allowed = allowed & padding_mask[:, None, None, :kv_len].bool()
+    if sequence_ids is not None:
+        allowed = allowed & (sequence_ids[:, None, :, None] == sequence_ids[:, None, None, :])
     min_dtype = torch.finfo(dtype).min
     return torch.where(allowed, torch.tensor(0.0, dtype=dtype), torch.tensor(min_dtype, dtype=dtype))
 
@@ -321,7 +334,7 @@ def decoder_layer(x: torch.Tensor, p: dict, layer_idx: int, cfg: DecoderConfig, 
 
 
 def model_forward(ids: torch.Tensor, p: dict, cfg: DecoderConfig, labels: torch.Tensor | None = None,
-                  padding_mask: torch.Tensor | None = None):
+                  padding_mask: torch.Tensor | None = None, position_ids: torch.Tensor | None = None):
     """LlamaModel.forward models/llama/modeling_llama.py:367-418 + LlamaForCausalLM.forward :438-490
     (Gemma2: scaled embedding :386-389, final logit softcap :527-530).  Returns (logits, loss, last_hidden)."""
     B, S = ids.shape
@@ -329,13 +342,17 @@ def model_forward(ids: torch.Tensor, p: dict, cfg: DecoderConfig, labels: torch.
     dtype = w_emb.dtype
     scale = cfg.hidden_size**0.5 if cfg.gemma_norm else None
     h = embedding(ids, w_emb, scale, cfg.pad_token_id)
-    position_ids = torch.arange(S)[None, :]
+    seq_ids = None
+    if position_ids is None:
+        position_ids = torch.arange(S)[None, :]
+    elif padding_mask is None:  # packed batches are only recognised without a padding mask (masking_utils.py:852-860)
+        seq_ids = packed_sequence_ids(position_ids.expand(B, -1))
     cos, sin = rope_tables(rope_inv_freq(cfg), position_ids, dtype)
     masks = {}
     for li in range(cfg.num_hidden_layers):
         win = cfg.layer_window(li)
         if win not in masks:
-            masks[win] = eager_mask(B, S, S, dtype, sliding_window=win, padding_mask=padding_mask)
+            masks[win] = eager_mask(B, S, S, dtype, sliding_window=win, padding_mask=padding_mask, sequence_ids=seq_ids)
         h = decoder_layer(h, p, li, cfg, cos, sin, masks[win])
     h = rms_norm(h, p["model.norm.weight"], cfg.rms_norm_eps, cfg.gemma_norm)
     w_head = w_emb if cfg.tie_word_embeddings else p["lm_head.weight"]

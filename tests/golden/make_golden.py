@@ -28,7 +28,7 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 torch.set_num_threads(4)
 
 
-def model_fixture(name, cls, cfg, dtype, B=2, S=24, pad=False):
+def model_fixture(name, cls, cfg, dtype, B=2, S=24, pad=False, packed=None):
     set_seed(42)
     extra = {"experts_implementation": "eager"} if hasattr(cfg, "num_local_experts") else {}  # per-expert loop = the eager path
     model = cls._from_config(cfg, attn_implementation="eager", dtype=dtype, **extra)
@@ -39,9 +39,14 @@ def model_fixture(name, cls, cfg, dtype, B=2, S=24, pad=False):
             if "norm" in n:
                 p.add_(torch.randn_like(p.float()).to(p.dtype) * 0.1)
     torch.manual_seed(0)
+    if packed is not None:  # padding-free packed batch: several sequences along one row, position_ids restart at each of them
+        B, S = 1, sum(packed)
     ids = torch.randint(0, cfg.vocab_size, (B, S))
     labels = ids.clone()
     kw = {}
+    if packed is not None:
+        kw["position_ids"] = torch.cat([torch.arange(n) for n in packed])[None]
+        kw["use_cache"] = False  # the reference only looks for packed sequences when no cache is in play (masking_utils.py:852-860)
     if pad:
         am = torch.ones(B, S, dtype=torch.long)
         am[1, -5:] = 0  # right padding on the second sequence
@@ -58,6 +63,7 @@ def model_fixture(name, cls, cfg, dtype, B=2, S=24, pad=False):
         "input_ids": ids,
         "labels": labels,
         "attention_mask": kw.get("attention_mask"),
+        "position_ids": kw.get("position_ids"),
         "logits": out.logits.detach().clone(),
         "loss": out.loss.detach().clone(),
         "last_hidden": out.hidden_states[-1].detach().clone(),
@@ -153,6 +159,7 @@ if __name__ == "__main__":
         jobs = {
             "llama_tiny": lambda: model_fixture(f"llama_tiny_{tag}", LlamaForCausalLM, llama_cfg(), dtype),
             "llama_tiny_padded": lambda: model_fixture(f"llama_tiny_padded_{tag}", LlamaForCausalLM, llama_cfg(), dtype, pad=True),
+            "llama_tiny_packed": lambda: model_fixture(f"llama_tiny_packed_{tag}", LlamaForCausalLM, llama_cfg(), dtype, packed=[7, 1, 11, 5]),
             "llama3rope_tiny": lambda: model_fixture(f"llama3rope_tiny_{tag}", LlamaForCausalLM, llama_cfg(rope_parameters={
                 "rope_type": "llama3", "rope_theta": 500000.0, "factor": 8.0, "low_freq_factor": 1.0, "high_freq_factor": 4.0,
                 "original_max_position_embeddings": 16}), dtype),

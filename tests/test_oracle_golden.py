@@ -91,7 +91,8 @@ def test_masks_match_reference(ops):
     assert torch.equal(O.eager_mask(2, 10, 10, m.dtype, sliding_window=4), ops["mask_sliding4"].expand(2, 1, 10, 10))
 
 
-MODELS = ["llama_tiny", "llama_tiny_padded", "llama3rope_tiny", "mistral_tiny", "gemma1_tiny", "gemma2_tiny", "mixtral_tiny"]
+MODELS = ["llama_tiny", "llama_tiny_padded", "llama_tiny_packed", "llama3rope_tiny", "mistral_tiny", "gemma1_tiny", "gemma2_tiny",
+          "mixtral_tiny"]
 
 
 @pytest.mark.parametrize("tag", ["fp32", "bf16"])
@@ -101,7 +102,8 @@ def test_model_forward_backward_matches_reference(name, tag):
     tol = TOL[tag]
     cfg = O.config_from_hf(fx["config"])
     params = {k: v.clone().requires_grad_(True) for k, v in fx["state_dict"].items()}
-    logits, loss, last = O.model_forward(fx["input_ids"], params, cfg, labels=fx["labels"], padding_mask=fx["attention_mask"])
+    logits, loss, last = O.model_forward(fx["input_ids"], params, cfg, labels=fx["labels"], padding_mask=fx["attention_mask"],
+                                         position_ids=fx.get("position_ids"))
     # embedding gather is integer indexing: bit-exact rows
     emb = O.embedding(fx["input_ids"], fx["state_dict"]["model.embed_tokens.weight"])
     assert torch.equal(emb[0, 0], fx["state_dict"]["model.embed_tokens.weight"][fx["input_ids"][0, 0]])
